@@ -1,0 +1,159 @@
+/*
+ * misa_b200.h -- C ABI of the B200-native EAM hot path for MISA-MD.
+ *
+ * This is the drop-in boundary. The reference defines its accelerator plug-in as
+ * eight C++ hook functions `${ARCH_NAME}_*` (reference src/arch/arch_imp.h:17-31, name-mangled through
+ * src/arch/arch_macros.h:10-11, dispatched from src/arch/hardware_accelerate.hpp:17-69 and
+ * src/arch/arch_env.hpp:15-25). Those hooks take C++ types (comm::BccDomain*, NeighbourIndex<AtomElement>*,
+ * eam*, AtomElement*); the thin C++ shim in arch_cuda/cuda_hooks.cpp flattens them to the plain pointers and
+ * sizes below and calls this ABI. Each entry point cites the hook / reference function it replaces.
+ *
+ * Conventions: every function returns 0 on success, a negative MISA_B200_E* code on failure (the reference's
+ * hooks return void and abort through MPI_Abort, src/simulation.cpp:100-102 -- the shim does the abort).
+ * All reals are fp64, lattice indices are the reference's linear index idx = (z*Sy + y)*Sx + x over the
+ * ghost-extended lattice with doubled x (reference src/atom/atom_list.h:117-119, src/atom/atom_set.cpp:18-26).
+ * `atoms` pointers are HOST pointers to the reference's 104-byte AtomElement AoS (src/atom/atom_element.h:18-41)
+ * unless stated otherwise. There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef MISA_B200_H
+#define MISA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MISA_B200_OK 0
+#define MISA_B200_ENODEV (-1)   /* no CUDA device / CUDA runtime error */
+#define MISA_B200_EINVAL (-2)   /* bad argument */
+#define MISA_B200_ESTATE (-3)   /* call order violated (e.g. compute before potential is set) */
+#define MISA_B200_ENCCL (-4)    /* NCCL unavailable or NCCL error */
+#define MISA_B200_EOVERFLOW (-5) /* inter-atom capacity exceeded */
+
+typedef struct misa_b200_ctx misa_b200_ctx;
+
+/* The fields of comm::BccDomain the path reads; the doubled-x twins and the
+ * ghost-extended sizes are derived inside. */
+typedef struct misa_b200_domain {
+    int64_t phase_space[3];        /* global box in cells */
+    int32_t grid_size[3];          /* process grid */
+    int32_t grid_coord[3];         /* this sub-box's coordinate in the grid */
+    int32_t sub_box_lattice_size[3]; /* owned cells per dimension (x NOT doubled) */
+    int32_t lattice_size_ghost[3];   /* ghost cells per side (x NOT doubled) */
+    int32_t sub_box_lattice_low[3];  /* sub_box_lattice_region.{x,y,z}_low (x NOT doubled) */
+    int32_t rank_id_neighbours[3][2]; /* [dim][LOWER=0/HIGHER=1] */
+    int32_t rank;                   /* own rank id */
+    double lattice_const;
+    double cutoff_radius_factor;
+    double meas_global_length[3];
+} misa_b200_domain;
+
+/* One tabulated function as libpot holds it after eam::interpolateFile(): n rows of 7 spline coefficients
+ * (row m = 1..n, row 0 unused), uniform grid with spacing 1/inv_dx starting at 0. */
+typedef struct misa_b200_table {
+    int32_t n;
+    double inv_dx;
+    const double *spline; /* (n+1)*7 doubles */
+} misa_b200_table;
+
+/* per-kernel timing slots for misa_b200_profile_read */
+enum {
+    MISA_B200_K_VERLET1 = 0, /* firststep + run-away test */
+    MISA_B200_K_HALO_X,      /* ghost fill: positions + types */
+    MISA_B200_K_RHO,         /* rho (+df when fused) */
+    MISA_B200_K_DF,
+    MISA_B200_K_HALO_DF,
+    MISA_B200_K_FORCE,
+    MISA_B200_K_VERLET2,
+    MISA_B200_K_INTER,       /* everything on the off-lattice path */
+    MISA_B200_K_XFER,        /* AoS<->SoA conversion kernels */
+    MISA_B200_K_COUNT
+};
+
+/* ---- environment: replaces cuda_env_init / cuda_env_clean (arch_imp.h:17-19; called from
+ *      frontend/misa_md.cpp:92,128) ------------------------------------------------------------ */
+int misa_b200_env_init(int device /* <0: LOCAL_RANK env or 0 */);
+int misa_b200_env_clean(void);
+int misa_b200_device_count(void);
+const char *misa_b200_last_error(void);
+
+/* ---- setup: replaces cuda_domain_init (arch_imp.h:21, call site simulation.cpp:52-54),
+ *      cuda_nei_offset_init (arch_imp.h:23, simulation.cpp:67-69), cuda_pot_init (arch_imp.h:25,
+ *      simulation.cpp:133) ------------------------------------------------------------------------ */
+int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out);
+int misa_b200_destroy(misa_b200_ctx *ctx);
+/* the four protected vectors of NeighbourIndex<AtomElement> (src/atom/neighbour_index.h:66-69) */
+int misa_b200_set_neighbour_offsets(misa_b200_ctx *ctx, const int64_t *even, size_t n_even, const int64_t *odd,
+                                    size_t n_odd, const int64_t *half_even, size_t n_half_even,
+                                    const int64_t *half_odd, size_t n_half_odd);
+/* Build the same four vectors inside the library (NeighbourIndex::make, neighbour_index.inl:13-76) --
+ * for hosts that do not run the reference's AtomSet. Returned copies are optional (may be NULL). */
+int misa_b200_make_neighbour_offsets(misa_b200_ctx *ctx, int cut_lattice, double cutoff_radius_factor);
+int misa_b200_get_neighbour_offsets(misa_b200_ctx *ctx, int which /*0 even,1 odd,2 half_even,3 half_odd*/,
+                                    int64_t *out, size_t cap, size_t *n);
+/* n_types species in atom_type enum order (Fe, Cu, Ni); phi is n_types*n_types, symmetric. */
+int misa_b200_set_potential(misa_b200_ctx *ctx, int n_types, const misa_b200_table *electron_density,
+                            const misa_b200_table *embedded, const misa_b200_table *phi);
+
+/* ---- compat mode: the three per-step hooks on the HOST AoS array -- replace cuda_eam_rho_calc /
+ *      cuda_eam_df_calc / cuda_eam_force_calc (arch_imp.h:27-31; call sites atom.cpp:160,294,321).
+ *      Post-conditions equal the CPU branches latRho / latDf / latForce (atom.cpp:151-192,286-309,311-358)
+ *      as seen after the host's reverse halos: owned sites receive their COMPLETE sums, ghost sites are
+ *      left untouched (SURVEY.md section 8b "required post-conditions"). ------------------------- */
+int misa_b200_eam_rho_calc(misa_b200_ctx *ctx, void *atoms, double cutoff_radius);
+int misa_b200_eam_df_calc(misa_b200_ctx *ctx, void *atoms, double cutoff_radius);
+int misa_b200_eam_force_calc(misa_b200_ctx *ctx, void *atoms, double cutoff_radius);
+/* page-lock the host AoS array once so the hook transfers run at PCIe speed (optional) */
+int misa_b200_host_register(void *ptr, size_t bytes);
+int misa_b200_host_unregister(void *ptr);
+
+/* ---- resident mode: state lives in HBM as SoA across steps; the host loop body of
+ *      simulation::simulate (simulation.cpp:164-194) runs on the device ------------------------- */
+int misa_b200_upload_atoms(misa_b200_ctx *ctx, const void *atoms);      /* whole ghost-extended array */
+int misa_b200_download_atoms(misa_b200_ctx *ctx, void *atoms);
+int misa_b200_upload_inter(misa_b200_ctx *ctx, const void *inter_atoms, size_t n); /* InterAtomList::inter_list */
+int misa_b200_download_inter(misa_b200_ctx *ctx, void *inter_atoms, size_t cap, size_t *n);
+int misa_b200_set_timestep(misa_b200_ctx *ctx, double dt);              /* NewtonMotion::setTimestepLength */
+int misa_b200_prepare(misa_b200_ctx *ctx);   /* exchangeAtomFirst + clearForce + computeEam (simulation.cpp:137-145) */
+int misa_b200_step(misa_b200_ctx *ctx, int n_steps); /* firststep .. secondstep, n times */
+int misa_b200_setv(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy); /* atom::setv */
+int misa_b200_collision_step(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy);
+int misa_b200_rescale(misa_b200_ctx *ctx, double t_set, double n_atoms_global); /* configuration::rescale (single rank sums; see thermo) */
+/* thermo[0]=sum m v^2 (configuration::mvv), [1]=E_pot local [eV] (ours), [2]=owned valid atoms,
+ * [3]=local inter atoms, [4]=ghost inter atoms, [5]=run-aways detected in the last step */
+int misa_b200_thermo(misa_b200_ctx *ctx, double out[6]);
+int misa_b200_sync(misa_b200_ctx *ctx);
+
+/* single passes on the resident state (kernel-level parity tests and profiling) */
+int misa_b200_pass_halo_x(misa_b200_ctx *ctx);  /* AtomList::exchangeAtom */
+int misa_b200_pass_clear(misa_b200_ctx *ctx);   /* atom::clearForce */
+int misa_b200_pass_rho(misa_b200_ctx *ctx);     /* latRho (+interRho), complete sums on owned sites */
+int misa_b200_pass_df(misa_b200_ctx *ctx);      /* latDf */
+int misa_b200_pass_halo_df(misa_b200_ctx *ctx); /* DfEmbedPacker exchange */
+int misa_b200_pass_force(misa_b200_ctx *ctx);   /* latForce (+interForce) */
+int misa_b200_pass_verlet1(misa_b200_ctx *ctx); /* NewtonMotion::firststep + atom::decide */
+int misa_b200_pass_verlet2(misa_b200_ctx *ctx); /* NewtonMotion::secondstep */
+
+/* options: 0 = off, 1 = on. "prune": use the 112-offset stencil whenever the 0.2a displacement invariant of
+ * atom::decide (atom.cpp:42) is verified on the device (default on); "fuse": rho+df fused when no inter atoms. */
+int misa_b200_set_option(misa_b200_ctx *ctx, const char *name, int value);
+
+/* ---- multi-GPU: one sub-box per GPU, NCCL send/recv between face neighbours (replaces libcomm's
+ *      comm::neiSendReceive over MPI; call sites atom.cpp:114,131,145, atom_list.cpp:45,53) ----- */
+int misa_b200_comm_unique_id(void *out128);
+int misa_b200_comm_init(misa_b200_ctx *ctx, const void *unique_id128, int rank, int n_ranks);
+int misa_b200_comm_destroy(misa_b200_ctx *ctx);
+
+/* ---- measurement: CUDA-event durations per kernel slot on the launching stream ---------------- */
+int misa_b200_profile_enable(misa_b200_ctx *ctx, int on);
+int misa_b200_profile_read(misa_b200_ctx *ctx, double ms_sum[MISA_B200_K_COUNT], int64_t launches[MISA_B200_K_COUNT]);
+int misa_b200_launch_count(misa_b200_ctx *ctx, int64_t *n); /* kernels launched since create */
+/* device time of n_steps through CUDA events on the context's stream (ms) */
+int misa_b200_timed_steps(misa_b200_ctx *ctx, int n_steps, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MISA_B200_H */

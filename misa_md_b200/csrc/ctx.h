@@ -1,0 +1,115 @@
+// misa_md_b200/csrc/ctx.h -- internal state of one sub-box on one B200 (not part of the C ABI).
+//
+// HBM layout: structure-of-arrays over the ghost-extended lattice, PARITY-SPLIT.
+// The reference's linear index idx = (z*Sy + y)*Sx + x (x doubled, even x = cube corner, odd x = body
+// centre; reference src/atom/atom_list.h:117-119) maps to the device index
+//     d(idx) = (idx >> 1) + (idx & 1) * H,        H = n_ext / 2
+// i.e. the first half of every array holds the corner sub-lattice as a plain [z][y][cx] cube and the second
+// half the body-centre sub-lattice. A warp then works on 32 consecutive cells of ONE sub-lattice: all lanes
+// share one neighbour-offset list and every neighbour load is a contiguous 256-byte segment.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include <string>
+#include "../../include/misa_b200.h"
+
+#define MISA_MAX_TYPES 3
+#define MISA_ROW 8  // spline rows padded from 7 to 8 doubles (64-byte rows)
+
+struct Geo {
+    int nx, ny, nz;     // owned cells
+    int gx, gy, gz;     // ghost cells per side
+    int sxc, sy, sz;    // ghost-extended cells: sxc = nx + 2gx (cells; the reference's Sx is 2*sxc)
+    int lo[3];          // sub_box_lattice_region low (cells)
+    long long H;        // n_ext / 2
+    long long n_ext;    // 2*sxc*sy*sz
+    long long n_cells_owned; // nx*ny*nz
+    double a;           // lattice constant
+    double rc2;         // (a*crf)^2 computed as cutoff_radius*cutoff_radius (reference src/atom.cpp:177)
+    double runaway2;    // pow(0.2*a, 2.0) (reference src/atom.cpp:42)
+};
+
+struct DevTables {
+    const double *elec;   // [n_types][n_r+1][8]
+    const double *embed;  // [n_types][n_rho+1][8]
+    const double *phi;    // [n_types*n_types][n_r+1][8]
+    int n_types, n_r, n_rho;
+    double inv_dr, inv_drho;
+};
+
+struct Soa {
+    double *x[3], *v[3], *f[3];
+    double *rho, *df;
+    int8_t *type;
+    unsigned long long *id;
+};
+
+struct InterSoa {  // off-lattice atoms: [0, n_local) local, [cap/2, cap/2 + n_ghost) ghost copies
+    double *x[3], *v[3], *f[3];
+    double *rho, *df;
+    int8_t *type;
+    unsigned long long *id;
+    int *site;   // device index of the Wigner-Seitz site (or -1)
+    int *next;   // linked list through a site bucket
+};
+
+struct HaloList {          // one (dim, dir) message
+    int n = 0;
+    int *d_send = nullptr; // device indices packed into the message, reference sendlist order
+    int *d_recv = nullptr; // device indices the mirrored message is unpacked into, reference recvlist order
+    double shift[3] = {0, 0, 0};
+};
+
+struct misa_b200_ctx {
+    misa_b200_domain dom;
+    Geo geo;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Soa s{};
+    unsigned char *d_aos = nullptr;       // staging for AoS <-> SoA (n_ext * 104 B)
+    // neighbour stencil, device-index space, per central parity
+    std::vector<int64_t> ref_off[4];      // even, odd, half_even, half_odd in REFERENCE index space
+    int n_full = 0, n_pruned = 0;
+    int *d_off_full = nullptr;            // [2][n_full]
+    int *d_off_pruned = nullptr;          // [2][n_pruned]
+    // potential
+    double *d_elec = nullptr, *d_embed = nullptr, *d_phi = nullptr;
+    DevTables tab{};
+    bool have_pot = false, have_off = false, have_atoms = false;
+    // halo
+    HaloList halo[3][2];
+    bool all_self = true;                 // 1x1x1 grid: every neighbour is this sub-box
+    int n_ghost_map = 0;                  // fused periodic ghost fill (all_self only)
+    int *d_ghost_dst = nullptr, *d_ghost_src = nullptr;
+    int8_t *d_ghost_shift = nullptr;      // per ghost site: shift code (3 x {-1,0,1}) packed
+    double *d_sendbuf[2] = {nullptr, nullptr}, *d_recvbuf[2] = {nullptr, nullptr};
+    size_t halo_buf_elems = 0;
+    // integrator
+    double dt = 0.001;
+    double dt_inv_m[MISA_MAX_TYPES] = {0, 0, 0};
+    // run-away / inter atoms
+    InterSoa inter{};
+    int inter_cap = 0;
+    int *d_counters = nullptr;            // [0] run-aways this step, [1] n_local inter, [2] n_ghost inter, [3] overflow, [4] invariant violations
+    int *h_counters = nullptr;            // pinned mirror
+    int n_inter_local = 0, n_inter_ghost = 0;
+    int *d_site_head = nullptr;           // n_ext ints, -1 = empty bucket
+    int *d_runaway = nullptr;             // device indices of this step's run-away sites
+    bool inter_active = false;            // any sub-box has off-lattice atoms this step (globally agreed)
+    double *d_reduce = nullptr;           // scratch for reductions (8 doubles)
+    double *h_reduce = nullptr;           // pinned
+    int last_runaways = 0;
+    // options
+    int opt_prune = 1, opt_fuse = 1;
+    bool invariant_ok = false;            // every valid lattice atom within 0.2a of its site (checked on device)
+    // NCCL
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    // profiling
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev[MISA_B200_K_COUNT];
+    double prof_ms[MISA_B200_K_COUNT] = {0};
+    int64_t prof_n[MISA_B200_K_COUNT] = {0};
+    int64_t launches = 0;
+};

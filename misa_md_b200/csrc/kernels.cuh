@@ -1,0 +1,423 @@
+// misa_md_b200/csrc/kernels.cuh -- sm_100a kernels of the EAM hot path (fp64, parity-split SoA).
+// Each kernel cites the reference CPU loop it replaces. See DESIGN.md section 4 for the per-kernel roofline.
+#pragma once
+#include "ctx.h"
+
+#define MISA_BLOCK 256
+
+// ---- index helpers ------------------------------------------------------------------------------
+// owned-cell ordinal c in [0, nx*ny*nz) of sub-lattice p -> device index
+__device__ __forceinline__ int owned_cell_to_dev(const Geo &g, int p, long long c, int &cx, int &y, int &z) {
+    cx = (int)(c % g.nx);
+    const long long r = c / g.nx;
+    y = (int)(r % g.ny);
+    z = (int)(r / g.ny);
+    return (int)(p * g.H + ((long long)(z + g.gz) * g.sy + (y + g.gy)) * g.sxc + (cx + g.gx));
+}
+__host__ __device__ __forceinline__ long long ref_to_dev(long long idx, long long H) { return (idx >> 1) + (idx & 1) * H; }
+__host__ __device__ __forceinline__ long long dev_to_ref(long long d, long long H) { return d >= H ? 2 * (d - H) + 1 : 2 * d; }
+
+// ---- spline evaluation: libpot InterpolationObject::findSpline + eam::{chargeDensity,dEmbedEnergy,toForce}
+//      restated (oracle/pot.c); rows are padded to 8 doubles. ---------------------------------------
+__device__ __forceinline__ const double *find_row(const double *__restrict__ tab, int n, double inv_dx, double x, double &p) {
+    p = x * inv_dx + 1.0;
+    int m = (int)p;
+    m = max(1, min(m, n - 1));
+    p -= (double)m;
+    p = fmin(p, 1.0);
+    return tab + (size_t)m * MISA_ROW;
+}
+
+__device__ __forceinline__ double charge_density(const DevTables &tb, int tj, double d2) {
+    double p;
+    const double r = sqrt(d2);
+    const double *s = find_row(tb.elec + (size_t)tj * (tb.n_r + 1) * MISA_ROW, tb.n_r, tb.inv_dr, r, p);
+    return ((s[3] * p + s[4]) * p + s[5]) * p + s[6];
+}
+
+__device__ __forceinline__ double d_embed(const DevTables &tb, int ti, double rho) {
+    double p;
+    const double *s = find_row(tb.embed + (size_t)ti * (tb.n_rho + 1) * MISA_ROW, tb.n_rho, tb.inv_drho, rho, p);
+    return (s[0] * p + s[1]) * p + s[2];
+}
+
+__device__ __forceinline__ double embed_energy(const DevTables &tb, int ti, double rho) {
+    double p;
+    const double *s = find_row(tb.embed + (size_t)ti * (tb.n_rho + 1) * MISA_ROW, tb.n_rho, tb.inv_drho, rho, p);
+    return ((s[3] * p + s[4]) * p + s[5]) * p + s[6];
+}
+
+__device__ __forceinline__ double to_force(const DevTables &tb, int ti, int tj, double d2, double df_i, double df_j) {
+    const double r = sqrt(d2);
+    double p;
+    const size_t tstride = (size_t)(tb.n_r + 1) * MISA_ROW;
+    const double *s = find_row(tb.phi + (size_t)(ti * tb.n_types + tj) * tstride, tb.n_r, tb.inv_dr, r, p);
+    const double z2 = ((s[3] * p + s[4]) * p + s[5]) * p + s[6];
+    const double z2p = (s[0] * p + s[1]) * p + s[2];
+    // elec tables share the r grid with phi: same row index m and fraction p
+    const size_t rowoff = (size_t)(s - (tb.phi + (size_t)(ti * tb.n_types + tj) * tstride));
+    const double *si = tb.elec + (size_t)ti * tstride + rowoff;
+    const double rho_p_from = (si[0] * p + si[1]) * p + si[2];
+    double rho_p_to = rho_p_from;
+    if (tj != ti) {
+        const double *sj = tb.elec + (size_t)tj * tstride + rowoff;
+        rho_p_to = (sj[0] * p + sj[1]) * p + sj[2];
+    }
+    const double recip = 1.0 / r;
+    const double phi = z2 * recip;
+    const double phip = z2p * recip - phi * recip;
+    const double psip = phip + (rho_p_from * df_j + rho_p_to * df_i);
+    return -psip * recip;
+}
+
+__device__ __forceinline__ double pair_energy(const DevTables &tb, int ti, int tj, double d2) {
+    const double r = sqrt(d2);
+    double p;
+    const size_t tstride = (size_t)(tb.n_r + 1) * MISA_ROW;
+    const double *s = find_row(tb.phi + (size_t)(ti * tb.n_types + tj) * tstride, tb.n_r, tb.inv_dr, r, p);
+    const double z2 = ((s[3] * p + s[4]) * p + s[5]) * p + s[6];
+    return z2 / r;
+}
+
+// ---- K8 clear: atom::clearForce (reference src/atom.cpp:86-100) -- all ghost-extended sites -------
+__global__ void __launch_bounds__(MISA_BLOCK) k_clear(long long n, double *__restrict__ fx, double *__restrict__ fy,
+                                                       double *__restrict__ fz, double *__restrict__ rho) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0; rho[i] = 0.0; }
+}
+
+// ---- K1 rho (+K2 df fused): atom::latRho / atom::latDf (reference src/atom.cpp:151-192,286-309) ----
+// Full-list GATHER: thread = one owned site, loops the parity's offset list, writes the complete sum
+// (the reference's half-list scatter + reverse halo, restated; SURVEY.md section 7 "hard part 2").
+// ACCUM: add to the existing rho (compat hook semantics, `rho +=`) instead of overwriting.
+template <bool FUSE_DF, bool ACCUM>
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_rho(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ offs, const int n_off, const int blocks_per_parity) {
+    extern __shared__ int s_off[];
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    for (int q = threadIdx.x; q < n_off; q += blockDim.x) s_off[q] = offs[p * n_off + q];
+    __syncthreads();
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells_owned) return;
+    int cx, y, z;
+    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+    const int ti = s.type[d];
+    if (ti < 0) {
+        if (!ACCUM) s.rho[d] = 0.0;
+        return;
+    }
+    const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+    double acc = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < n_off; q++) {
+        const int j = d + s_off[q];
+        const int tj = s.type[j];
+        const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (tj >= 0 && d2 < g.rc2) acc += charge_density(tb, tj, d2);
+    }
+    if (ACCUM) acc += s.rho[d];
+    s.rho[d] = acc;
+    if (FUSE_DF) s.df[d] = d_embed(tb, ti, acc);
+}
+
+// ---- K2 df: atom::latDf (reference src/atom.cpp:286-309) -------------------------------------------
+__global__ void __launch_bounds__(MISA_BLOCK) k_df(const Geo g, const Soa s, const DevTables tb, const int blocks_per_parity) {
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells_owned) return;
+    int cx, y, z;
+    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+    const int ti = s.type[d];
+    if (ti < 0) return;
+    s.df[d] = d_embed(tb, ti, s.rho[d]);
+}
+
+// ---- K3 force: atom::latForce (reference src/atom.cpp:311-358) -------------------------------------
+// Full-list gather; f_i = sum_j (x_i - x_j) * toForce(t_i, t_j, r^2, df_i, df_j). toForce is symmetric in
+// (i,j) so this equals the reference's two-sided half-list update after its force reverse halo.
+// FUSE_V2: also apply NewtonMotion::secondstep (v += dt/(2m) f) to the same site (f is complete in-thread).
+template <bool ACCUM>
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_force(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ offs, const int n_off, const int blocks_per_parity) {
+    extern __shared__ int s_off[];
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    for (int q = threadIdx.x; q < n_off; q += blockDim.x) s_off[q] = offs[p * n_off + q];
+    __syncthreads();
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells_owned) return;
+    int cx, y, z;
+    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+    const int ti = s.type[d];
+    if (ti < 0) {
+        if (!ACCUM) { s.f[0][d] = 0.0; s.f[1][d] = 0.0; s.f[2][d] = 0.0; }
+        return;
+    }
+    const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+    const double dfi = s.df[d];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < n_off; q++) {
+        const int j = d + s_off[q];
+        const int tj = s.type[j];
+        const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (tj >= 0 && d2 < g.rc2) {
+            const double fp = to_force(tb, ti, tj, d2, dfi, s.df[j]);
+            fx += dx * fp; fy += dy * fp; fz += dz * fp;
+        }
+    }
+    if (ACCUM) { fx += s.f[0][d]; fy += s.f[1][d]; fz += s.f[2][d]; }
+    s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz;
+}
+
+// ---- K4 verlet-1 + run-away test: NewtonMotion::firststep (reference src/newton_motion.cpp:30-55) and the
+//      displacement test of atom::decide (reference src/atom.cpp:27-52). Operation order is the reference's,
+//      with explicit round-to-nearest mul/add (no FMA contraction) so x, v and the run-away decision are
+//      bit-exact. Run-aways are appended to `runaway_sites` (device indices); the site is vacated by
+//      k_decide_vacate after the list has been sorted into the reference's k,j,i order. ------------------
+struct VerletPar { double dt; double c[MISA_MAX_TYPES]; };
+
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
+          int *__restrict__ runaway_sites, const int runaway_cap) {
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells_owned) return;
+    int cx, y, z;
+    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+    const int t = s.type[d];
+    if (t < 0) return;
+    const double cm = vp.c[t];
+    double x[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double v = __dadd_rn(s.v[k][d], __dmul_rn(cm, s.f[k][d]));
+        s.v[k][d] = v;
+        x[k] = __dadd_rn(s.x[k][d], __dmul_rn(vp.dt, v));
+        s.x[k][d] = x[k];
+    }
+    // ideal site, reference src/atom.cpp:34-38: i is the doubled-x sub-box index
+    const long long i = 2LL * cx + p;
+    const double xt = __dmul_rn(__dmul_rn((double)(i + 2LL * g.lo[0]), 0.5), g.a);
+    const double yt = __dmul_rn(__dadd_rn((double)((long long)y + g.lo[1]), (double)(i % 2) * 0.5), g.a);
+    const double zt = __dmul_rn(__dadd_rn((double)((long long)z + g.lo[2]), (double)(i % 2) * 0.5), g.a);
+    const double ex = __dadd_rn(x[0], -xt), ey = __dadd_rn(x[1], -yt), ez = __dadd_rn(x[2], -zt);
+    double dist = __dmul_rn(ex, ex);
+    dist = __dadd_rn(dist, __dmul_rn(ey, ey));
+    dist = __dadd_rn(dist, __dmul_rn(ez, ez));
+    if (dist > g.runaway2) {
+        const int slot = atomicAdd(&counters[0], 1);
+        if (slot < runaway_cap) runaway_sites[slot] = d;
+        else atomicExch(&counters[3], 1);
+    }
+}
+
+// ---- K5 verlet-2: NewtonMotion::secondstep (reference src/newton_motion.cpp:57-74) -------------------
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_verlet2(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity) {
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells_owned) return;
+    int cx, y, z;
+    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+    const int t = s.type[d];
+    if (t < 0) return;
+    const double cm = vp.c[t];
+#pragma unroll
+    for (int k = 0; k < 3; k++) s.v[k][d] = __dadd_rn(s.v[k][d], __dmul_rn(cm, s.f[k][d]));
+}
+
+// ---- K6 halo: LatPacker / DfEmbedPacker (reference src/pack/lat_particle_packer.cpp:153-193,
+//      src/pack/df_embed_packer.cpp:27-68) as device pack / unpack / local periodic copy -------------------
+// message layout for positions: 4 doubles per site {x+shift, y+shift, z+shift, type} (LatParticleData, 32 B)
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_pack_x(const int n, const int *__restrict__ send, const Soa s, const double sx, const double sy, const double sz,
+         double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = send[i];
+    double4 r;
+    r.x = __dadd_rn(s.x[0][d], sx);
+    r.y = __dadd_rn(s.x[1][d], sy);
+    r.z = __dadd_rn(s.x[2][d], sz);
+    r.w = (double)s.type[d];
+    reinterpret_cast<double4 *>(buf)[i] = r;
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_unpack_x(const int n, const int *__restrict__ recv, const Soa s, const double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = recv[i];
+    const double4 r = reinterpret_cast<const double4 *>(buf)[i];
+    s.x[0][d] = r.x; s.x[1][d] = r.y; s.x[2][d] = r.z;
+    s.type[d] = (int8_t)(int)r.w;
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_copy_x(const int n, const int *__restrict__ send, const int *__restrict__ recv, const Soa s, const double sx,
+         const double sy, const double sz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = send[i], b = recv[i];
+    s.x[0][b] = __dadd_rn(s.x[0][a], sx);
+    s.x[1][b] = __dadd_rn(s.x[1][a], sy);
+    s.x[2][b] = __dadd_rn(s.x[2][a], sz);
+    s.type[b] = s.type[a];
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_pack_1(const int n, const int *__restrict__ send, const double *__restrict__ field, double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = field[send[i]];
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_unpack_1(const int n, const int *__restrict__ recv, double *__restrict__ field, const double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) field[recv[i]] = buf[i];
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_copy_1(const int n, const int *__restrict__ send, const int *__restrict__ recv, double *__restrict__ field) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) field[recv[i]] = field[send[i]];
+}
+// fused periodic ghost fill for a 1x1x1 process grid: the three staged self-exchanges composed into one map
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_ghost_fill_x(const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code,
+               const Soa s, const double lx, const double ly, const double lz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = src[i], b = dst[i];
+    const int cd = code[i]; // (sx+1) + 3*(sy+1) + 9*(sz+1), shifts applied in x,y,z stage order
+    const int kx = cd % 3 - 1, ky = (cd / 3) % 3 - 1, kz = cd / 9 - 1;
+    double x = s.x[0][a], y = s.x[1][a], z = s.x[2][a];
+    if (kx) x = __dadd_rn(x, kx > 0 ? lx : -lx);
+    if (ky) y = __dadd_rn(y, ky > 0 ? ly : -ly);
+    if (kz) z = __dadd_rn(z, kz > 0 ? lz : -lz);
+    s.x[0][b] = x; s.x[1][b] = y; s.x[2][b] = z;
+    s.type[b] = s.type[a];
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_ghost_fill_1(const int n, const int *__restrict__ dst, const int *__restrict__ src, double *__restrict__ field) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) field[dst[i]] = field[src[i]];
+}
+
+// ---- AoS <-> SoA (compat hooks and upload/download): AtomElement is 13 x 8-byte words ---------------
+// word: 0 id | 1 type(+pad) | 2-4 x | 5-7 v | 8-10 f | 11 rho | 12 df   (reference src/atom/atom_element.h:18-41)
+#define AOS_WORDS 13
+enum { F_ID = 1, F_TYPE = 2, F_X = 4, F_V = 8, F_F = 16, F_RHO = 32, F_DF = 64, F_ALL = 127 };
+
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_aos_to_soa(const long long n_ext, const long long H, const unsigned long long *__restrict__ aos, const Soa s, const int fields) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_ext) return;
+    const long long d = ref_to_dev(idx, H);
+    const unsigned long long *w = aos + idx * AOS_WORDS;
+    if (fields & F_ID) s.id[d] = w[0];
+    if (fields & F_TYPE) s.type[d] = (int8_t)(int)(unsigned)(w[1] & 0xffffffffull);
+    if (fields & F_X) { s.x[0][d] = __longlong_as_double(w[2]); s.x[1][d] = __longlong_as_double(w[3]); s.x[2][d] = __longlong_as_double(w[4]); }
+    if (fields & F_V) { s.v[0][d] = __longlong_as_double(w[5]); s.v[1][d] = __longlong_as_double(w[6]); s.v[2][d] = __longlong_as_double(w[7]); }
+    if (fields & F_F) { s.f[0][d] = __longlong_as_double(w[8]); s.f[1][d] = __longlong_as_double(w[9]); s.f[2][d] = __longlong_as_double(w[10]); }
+    if (fields & F_RHO) s.rho[d] = __longlong_as_double(w[11]);
+    if (fields & F_DF) s.df[d] = __longlong_as_double(w[12]);
+}
+// owned_only: write back only sites inside the sub-box (ghost records of the host array stay untouched)
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_soa_to_aos(const Geo g, unsigned long long *__restrict__ aos, const Soa s, const int fields, const int owned_only) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.n_ext) return;
+    if (owned_only) {
+        const int sx = 2 * g.sxc;
+        const int x = (int)(idx % sx);
+        const long long r = idx / sx;
+        const int y = (int)(r % g.sy), z = (int)(r / g.sy);
+        if (x < 2 * g.gx || x >= 2 * (g.gx + g.nx) || y < g.gy || y >= g.gy + g.ny || z < g.gz || z >= g.gz + g.nz) return;
+    }
+    const long long d = ref_to_dev(idx, g.H);
+    unsigned long long *w = aos + idx * AOS_WORDS;
+    if (fields & F_ID) w[0] = s.id[d];
+    if (fields & F_TYPE) w[1] = (w[1] & 0xffffffff00000000ull) | (unsigned long long)(unsigned)(int)s.type[d];
+    if (fields & F_X) { w[2] = __double_as_longlong(s.x[0][d]); w[3] = __double_as_longlong(s.x[1][d]); w[4] = __double_as_longlong(s.x[2][d]); }
+    if (fields & F_V) { w[5] = __double_as_longlong(s.v[0][d]); w[6] = __double_as_longlong(s.v[1][d]); w[7] = __double_as_longlong(s.v[2][d]); }
+    if (fields & F_F) { w[8] = __double_as_longlong(s.f[0][d]); w[9] = __double_as_longlong(s.f[1][d]); w[10] = __double_as_longlong(s.f[2][d]); }
+    if (fields & F_RHO) w[11] = __double_as_longlong(s.rho[d]);
+    if (fields & F_DF) w[12] = __double_as_longlong(s.df[d]);
+}
+
+// ---- 0.2a invariant check (compat hooks): is every valid owned atom within 0.2a of its site? ---------
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_check_invariant(const Geo g, const Soa s, const int blocks_per_parity, int *__restrict__ counters) {
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    if (c >= g.n_cells_owned) return;
+    int cx, y, z;
+    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+    if (s.type[d] < 0) return;
+    const long long i = 2LL * cx + p;
+    const double xt = (double)(i + 2LL * g.lo[0]) * 0.5 * g.a;
+    const double yt = ((double)((long long)y + g.lo[1]) + (double)(i % 2) * 0.5) * g.a;
+    const double zt = ((double)((long long)z + g.lo[2]) + (double)(i % 2) * 0.5) * g.a;
+    const double ex = s.x[0][d] - xt, ey = s.x[1][d] - yt, ez = s.x[2][d] - zt;
+    // strict margin: anything not clearly inside 0.2a counts as a violation
+    if (ex * ex + ey * ey + ez * ez > g.runaway2 * (1.0 - 1e-9)) atomicAdd(&counters[4], 1);
+}
+
+// ---- diagnostics: sum m v^2 (configuration::mvv, reference src/system_configuration.cpp:61-84), E_pot ---
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[MISA_BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < MISA_BLOCK / 32 ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    __syncthreads();
+    return v;
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_thermo(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ offs, const int n_off,
+         const int blocks_per_parity, const double m0, const double m1, const double m2, double *__restrict__ out) {
+    extern __shared__ int s_off[];
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    for (int q = threadIdx.x; q < n_off; q += blockDim.x) s_off[q] = offs[p * n_off + q];
+    __syncthreads();
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    double mvv = 0.0, pe = 0.0, cnt = 0.0;
+    if (c < g.n_cells_owned) {
+        int cx, y, z;
+        const int d = owned_cell_to_dev(g, p, c, cx, y, z);
+        const int ti = s.type[d];
+        if (ti >= 0) {
+            const double m = ti == 0 ? m0 : (ti == 1 ? m1 : m2);
+            mvv = (s.v[0][d] * s.v[0][d] + s.v[1][d] * s.v[1][d] + s.v[2][d] * s.v[2][d]) * m;
+            cnt = 1.0;
+            pe = embed_energy(tb, ti, s.rho[d]);
+            const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+            double e2 = 0.0;
+            for (int q = 0; q < n_off; q++) {
+                const int j = d + s_off[q];
+                const int tj = s.type[j];
+                const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+                const double d2 = dx * dx + dy * dy + dz * dz;
+                if (tj >= 0 && d2 < g.rc2) e2 += pair_energy(tb, ti, tj, d2);
+            }
+            pe += 0.5 * e2;
+        }
+    }
+    mvv = block_sum(mvv);
+    pe = block_sum(pe);
+    cnt = block_sum(cnt);
+    if (threadIdx.x == 0) { atomicAdd(&out[0], mvv); atomicAdd(&out[1], pe); atomicAdd(&out[2], cnt); }
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_scale_v(const long long n, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz, const double fac) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { vx[i] *= fac; vy[i] *= fac; vz[i] *= fac; }
+}

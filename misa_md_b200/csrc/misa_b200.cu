@@ -1,0 +1,899 @@
+// misa_md_b200/csrc/misa_b200.cu -- host side of the C ABI declared in include/misa_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ctx.h"
+#include "util.cuh"
+#include "kernels.cuh"
+#include "nccl_dl.cuh"
+#include "inter.cuh"
+
+extern "C" const char *misa_b200_last_error(void) { return g_err.c_str(); }
+
+// reference src/types/pre_define.h:11-19, src/types/atom_types.h:17-19
+static const double kMvv2e = 1.0364269e-4;
+static const double kFtm2v = 1.0 / 1.0364269e-4;
+static const double kBoltz = 8.617343e-5;
+static const double kMass[MISA_MAX_TYPES] = {55.845, 63.546, 58.6934};
+
+static int g_device = -1;
+
+extern "C" int misa_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int misa_b200_env_init(int device) {
+    int n = misa_b200_device_count();
+    REQ(n > 0, MISA_B200_ENODEV, "misa_b200_env_init: no CUDA device visible (there is no CPU fallback)");
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % n : 0;
+    }
+    REQ(device < n, MISA_B200_EINVAL, "misa_b200_env_init: device index out of range");
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));
+    g_device = device;
+    return MISA_B200_OK;
+}
+
+extern "C" int misa_b200_env_clean(void) {
+    if (g_device >= 0) cudaDeviceSynchronize();
+    g_device = -1;
+    return MISA_B200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// profiling helpers: CUDA events on the launching stream around each kernel slot
+// -------------------------------------------------------------------------------------------------
+struct Slot {
+    misa_b200_ctx *c;
+    int k;
+    Slot(misa_b200_ctx *ctx, int slot) : c(ctx), k(slot) {
+        if (c->prof_on) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, c->stream);
+            c->prof_ev[k].push_back(e);
+        }
+    }
+    ~Slot() {
+        if (c->prof_on) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, c->stream);
+            c->prof_ev[k].push_back(e);
+        }
+    }
+};
+
+static inline int nblk(long long n) { return (int)((n + MISA_BLOCK - 1) / MISA_BLOCK); }
+
+// -------------------------------------------------------------------------------------------------
+// create / destroy
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int dmalloc(T **p, size_t n) {
+    CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+
+static void build_halo_lists_host(const misa_b200_ctx *c, std::vector<int> send[3][2], std::vector<int> recv[3][2]) {
+    // sendlist: comm::fwCommLocalRegion as used at reference src/atom/atom_list.cpp:33-40;
+    // recvlist: slabs of LatPackerFirst::onReceive, reference src/pack/lat_particle_packer.cpp:65-76,97-108,128-139.
+    const Geo &g = c->geo;
+    const int gh[3] = {2 * g.gx, g.gy, g.gz}, bx[3] = {2 * g.nx, g.ny, g.nz}, ex[3] = {2 * g.sxc, g.sy, g.sz};
+    for (int d = 0; d < 3; d++)
+        for (int dir = 0; dir < 2; dir++) {
+            int slo[3], shi[3], rlo[3], rhi[3];
+            for (int k = 0; k < 3; k++) {
+                if (k == d) {
+                    if (dir == 0) { slo[k] = gh[k]; shi[k] = 2 * gh[k]; rlo[k] = gh[k] + bx[k]; rhi[k] = ex[k]; }
+                    else { slo[k] = bx[k]; shi[k] = bx[k] + gh[k]; rlo[k] = 0; rhi[k] = gh[k]; }
+                } else if (k < d) { slo[k] = rlo[k] = 0; shi[k] = rhi[k] = ex[k]; }
+                else { slo[k] = rlo[k] = gh[k]; shi[k] = rhi[k] = gh[k] + bx[k]; }
+            }
+            auto fill = [&](std::vector<int> &v, const int *lo, const int *hi) {
+                v.clear();
+                for (int z = lo[2]; z < hi[2]; z++)
+                    for (int y = lo[1]; y < hi[1]; y++)
+                        for (int x = lo[0]; x < hi[0]; x++) {
+                            const long long idx = ((long long)z * ex[1] + y) * ex[0] + x;
+                            v.push_back((int)ref_to_dev(idx, g.H));
+                        }
+            };
+            fill(send[d][dir], slo, shi);
+            fill(recv[d][dir], rlo, rhi);
+        }
+}
+
+extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out) {
+    REQ(dom && out, MISA_B200_EINVAL, "misa_b200_create: null argument");
+    if (g_device < 0) TRY(misa_b200_env_init(-1));
+    misa_b200_ctx *c = new misa_b200_ctx();
+    c->dom = *dom;
+    c->device = g_device;
+    Geo &g = c->geo;
+    g.nx = dom->sub_box_lattice_size[0]; g.ny = dom->sub_box_lattice_size[1]; g.nz = dom->sub_box_lattice_size[2];
+    g.gx = dom->lattice_size_ghost[0]; g.gy = dom->lattice_size_ghost[1]; g.gz = dom->lattice_size_ghost[2];
+    g.sxc = g.nx + 2 * g.gx; g.sy = g.ny + 2 * g.gy; g.sz = g.nz + 2 * g.gz;
+    for (int k = 0; k < 3; k++) g.lo[k] = dom->sub_box_lattice_low[k];
+    g.n_ext = 2LL * g.sxc * g.sy * g.sz;
+    g.H = g.n_ext / 2;
+    g.n_cells_owned = (long long)g.nx * g.ny * g.nz;
+    g.a = dom->lattice_const;
+    const double cutoff_radius = dom->lattice_const * dom->cutoff_radius_factor; // reference src/atom.cpp:15
+    g.rc2 = cutoff_radius * cutoff_radius;
+    g.runaway2 = pow(0.2 * dom->lattice_const, 2.0);                             // reference src/atom.cpp:42
+    if (g.nx <= 0 || g.ny <= 0 || g.nz <= 0 || g.gx < 1 || g.n_ext >= (1LL << 31)) {
+        delete c;
+        return fail(MISA_B200_EINVAL, "misa_b200_create: bad sub-box sizes");
+    }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t n = (size_t)g.n_ext;
+    for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.x[k], n)); TRY(dmalloc(&c->s.v[k], n)); TRY(dmalloc(&c->s.f[k], n)); }
+    TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.df, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n));
+    for (int k = 0; k < 3; k++) { CU(cudaMemset(c->s.x[k], 0, n * 8)); CU(cudaMemset(c->s.v[k], 0, n * 8)); CU(cudaMemset(c->s.f[k], 0, n * 8)); }
+    CU(cudaMemset(c->s.rho, 0, n * 8)); CU(cudaMemset(c->s.df, 0, n * 8)); CU(cudaMemset(c->s.type, 0xff, n)); CU(cudaMemset(c->s.id, 0, n * 8));
+    TRY(dmalloc(&c->d_counters, 16));
+    CU(cudaMemset(c->d_counters, 0, 16 * sizeof(int)));
+    CU(cudaMallocHost((void **)&c->h_counters, 16 * sizeof(int)));
+    TRY(dmalloc(&c->d_reduce, 8));
+    CU(cudaMallocHost((void **)&c->h_reduce, 8 * sizeof(double)));
+
+    // halo lists
+    std::vector<int> send[3][2], recv[3][2];
+    build_halo_lists_host(c, send, recv);
+    c->all_self = true;
+    size_t max_n = 0;
+    for (int d = 0; d < 3; d++)
+        for (int dir = 0; dir < 2; dir++) {
+            HaloList &h = c->halo[d][dir];
+            h.n = (int)send[d][dir].size();
+            max_n = std::max(max_n, (size_t)h.n);
+            TRY(dmalloc(&h.d_send, (size_t)h.n)); TRY(dmalloc(&h.d_recv, (size_t)h.n));
+            CU(cudaMemcpy(h.d_send, send[d][dir].data(), h.n * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(h.d_recv, recv[d][dir].data(), h.n * sizeof(int), cudaMemcpyHostToDevice));
+            // periodic image shift, reference src/pack/lat_particle_packer.cpp:22-32
+            if (dom->grid_coord[d] == 0 && dir == 0) h.shift[d] = dom->meas_global_length[d];
+            if (dom->grid_coord[d] == dom->grid_size[d] - 1 && dir == 1) h.shift[d] = -dom->meas_global_length[d];
+            if (dom->grid_size[d] != 1) c->all_self = false;
+        }
+    c->halo_buf_elems = max_n * 4;
+    for (int dir = 0; dir < 2; dir++) { TRY(dmalloc(&c->d_sendbuf[dir], c->halo_buf_elems)); TRY(dmalloc(&c->d_recvbuf[dir], c->halo_buf_elems)); }
+    if (c->all_self) {
+        // compose the three staged self-exchanges into one ghost <- owned map
+        std::vector<int> src_of(n), code(n, 13); // 13 = (0+1) + 3*(0+1) + 9*(0+1)
+        for (size_t i = 0; i < n; i++) src_of[i] = (int)i;
+        std::vector<int> dst_list;
+        static const int mul[3] = {1, 3, 9};
+        for (int d = 0; d < 3; d++)
+            for (int dir = 0; dir < 2; dir++)
+                for (size_t i = 0; i < send[d][dir].size(); i++) {
+                    const int a = send[d][dir][i], b = recv[d][dir][i];
+                    src_of[b] = src_of[a];
+                    code[b] = code[a] + mul[d] * (dir == 0 ? 1 : -1);
+                    dst_list.push_back(b);
+                }
+        std::sort(dst_list.begin(), dst_list.end());
+        std::vector<int> srcs(dst_list.size());
+        std::vector<int8_t> codes(dst_list.size());
+        for (size_t i = 0; i < dst_list.size(); i++) { srcs[i] = src_of[dst_list[i]]; codes[i] = (int8_t)code[dst_list[i]]; }
+        c->n_ghost_map = (int)dst_list.size();
+        TRY(dmalloc(&c->d_ghost_dst, dst_list.size())); TRY(dmalloc(&c->d_ghost_src, dst_list.size())); TRY(dmalloc(&c->d_ghost_shift, dst_list.size()));
+        CU(cudaMemcpy(c->d_ghost_dst, dst_list.data(), dst_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_ghost_src, srcs.data(), srcs.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_ghost_shift, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+    }
+    TRY(inter_alloc(c, 1 << 16));
+    misa_b200_set_timestep(c, 0.001);
+    *out = c;
+    return MISA_B200_OK;
+}
+
+extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
+    if (!c) return MISA_B200_OK;
+    cudaStreamSynchronize(c->stream);
+    misa_b200_comm_destroy(c);
+    for (int k = 0; k < 3; k++) { cudaFree(c->s.x[k]); cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
+    cudaFree(c->s.rho); cudaFree(c->s.df); cudaFree(c->s.type); cudaFree(c->s.id);
+    cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_pruned);
+    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi);
+    for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
+    for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
+    cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
+    cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
+    inter_free(c);
+    for (int k = 0; k < MISA_B200_K_COUNT; k++) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return MISA_B200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// neighbour stencil
+// -------------------------------------------------------------------------------------------------
+// reference offset (linear, doubled-x) of parity p -> device-index offset; see ctx.h
+static int ref_off_to_dev(long long off, int p, long long H) {
+    if (p == 0) return (int)((off >> 1) + (off & 1) * H);
+    if ((off & 1) == 0) return (int)(off / 2);
+    return (int)((off + 1) / 2 - H);
+}
+// decode a reference offset into (dx, dy, dz) and return the squared SITE separation in units of a^2
+static double off_site_r2(long long off, int p, const Geo &g) {
+    const long long sx = 2LL * g.sxc, sy = g.sy;
+    long long dx = ((off % sx) + sx + sx / 2) % sx - sx / 2;
+    long long r = (off - dx) / sx;
+    long long dy = ((r % sy) + sy + sy / 2) % sy - sy / 2;
+    long long dz = (r - dy) / sy;
+    const double half = (dx & 1) ? (p == 0 ? 0.5 : -0.5) : 0.0; // odd dx switches sub-lattice
+    const double X = 0.5 * (double)dx, Y = (double)dy + half, Z = (double)dz + half;
+    return X * X + Y * Y + Z * Z;
+}
+
+static int upload_offsets(misa_b200_ctx *c) {
+    const Geo &g = c->geo;
+    REQ(c->ref_off[0].size() == c->ref_off[1].size() && !c->ref_off[0].empty(), MISA_B200_EINVAL,
+        "neighbour offsets: even/odd lists must be non-empty and of equal length");
+    c->n_full = (int)c->ref_off[0].size();
+    std::vector<int> full(2 * (size_t)c->n_full), pruned[2];
+    // pairs of LATTICE atoms can only be within the cutoff if their sites are closer than crf + 2*0.2
+    // (atom::decide keeps every lattice atom within 0.2a of its site, reference src/atom.cpp:42)
+    const double lim = c->dom.cutoff_radius_factor + 0.4;
+    for (int p = 0; p < 2; p++)
+        for (int q = 0; q < c->n_full; q++) {
+            const long long off = c->ref_off[p][q];
+            const int dv = ref_off_to_dev(off, p, g.H);
+            full[(size_t)p * c->n_full + q] = dv;
+            if (off_site_r2(off, p, g) < lim * lim) pruned[p].push_back(dv);
+        }
+    REQ(pruned[0].size() == pruned[1].size(), MISA_B200_EINVAL, "neighbour offsets: pruned lists differ in length");
+    c->n_pruned = (int)pruned[0].size();
+    cudaFree(c->d_off_full); cudaFree(c->d_off_pruned);
+    c->d_off_full = c->d_off_pruned = nullptr;
+    TRY(dmalloc(&c->d_off_full, full.size()));
+    TRY(dmalloc(&c->d_off_pruned, 2 * (size_t)c->n_pruned));
+    CU(cudaMemcpy(c->d_off_full, full.data(), full.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_off_pruned, pruned[0].data(), c->n_pruned * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_off_pruned + c->n_pruned, pruned[1].data(), c->n_pruned * sizeof(int), cudaMemcpyHostToDevice));
+    c->have_off = true;
+    return MISA_B200_OK;
+}
+
+extern "C" int misa_b200_set_neighbour_offsets(misa_b200_ctx *c, const int64_t *even, size_t n_even, const int64_t *odd,
+                                               size_t n_odd, const int64_t *half_even, size_t n_half_even,
+                                               const int64_t *half_odd, size_t n_half_odd) {
+    REQ(c && even && odd, MISA_B200_EINVAL, "misa_b200_set_neighbour_offsets: null argument");
+    c->ref_off[0].assign(even, even + n_even);
+    c->ref_off[1].assign(odd, odd + n_odd);
+    if (half_even) c->ref_off[2].assign(half_even, half_even + n_half_even);
+    if (half_odd) c->ref_off[3].assign(half_odd, half_odd + n_half_odd);
+    return upload_offsets(c);
+}
+
+extern "C" int misa_b200_make_neighbour_offsets(misa_b200_ctx *c, int cut_lattice, double crf) {
+    // NeighbourIndex<T>::make, reference src/atom/neighbour_index.inl:13-76 (C++ % keeps the sign of xIndex)
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    const Geo &g = c->geo;
+    const long long sx = 2LL * g.sxc, sy = g.sy;
+    const double lim = crf + 2 * 0.5; // config::nei_lat_cutoff, reference src/md_building_config.h.in:24-29
+    for (int v = 0; v < 4; v++) c->ref_off[v].clear();
+    for (int p = 0; p < 2; p++) {
+        const double sgn = p == 0 ? 1.0 : -1.0;
+        for (long long zi = -cut_lattice - 1; zi <= cut_lattice + 1; zi++)
+            for (long long yi = -cut_lattice - 1; yi <= cut_lattice + 1; yi++)
+                for (long long xi = -2 * cut_lattice - 2; xi <= 2 * cut_lattice + 2; xi++) {
+                    const double z = (double)zi + sgn * (((double)(xi % 2)) / 2);
+                    const double y = (double)yi + sgn * (((double)(xi % 2)) / 2);
+                    const double x = ((double)xi) / 2;
+                    const double r = x * x + y * y + z * z;
+                    if (r < lim * lim && r > 0) {
+                        const bool neg_odd = xi < 0 && xi % 2 != 0;
+                        const long long iy = neg_odd ? yi - (long long)sgn : yi, iz = neg_odd ? zi - (long long)sgn : zi;
+                        const long long off = (iz * sy + iy) * sx + xi;
+                        c->ref_off[p].push_back(off);
+                        const bool positive = z > 0 || (z == 0 && (y > 0 || (y == 0 && x > 0)));
+                        if (positive) c->ref_off[2 + p].push_back(off);
+                    }
+                }
+    }
+    return upload_offsets(c);
+}
+
+extern "C" int misa_b200_get_neighbour_offsets(misa_b200_ctx *c, int which, int64_t *out, size_t cap, size_t *n) {
+    REQ(c && which >= 0 && which < 4 && n, MISA_B200_EINVAL, "misa_b200_get_neighbour_offsets: bad argument");
+    *n = c->ref_off[which].size();
+    if (out) for (size_t i = 0; i < std::min(cap, *n); i++) out[i] = c->ref_off[which][i];
+    return MISA_B200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// potential tables
+// -------------------------------------------------------------------------------------------------
+static int upload_tables(const misa_b200_table *t, int count, double **dptr, int *n_out, double *inv_out, const char *what) {
+    const int n = t[0].n;
+    for (int i = 0; i < count; i++)
+        REQ(t[i].spline && t[i].n == n && t[i].inv_dx == t[0].inv_dx, MISA_B200_EINVAL,
+            std::string("misa_b200_set_potential: ") + what + " tables must share one grid");
+    std::vector<double> host((size_t)count * (n + 1) * MISA_ROW, 0.0);
+    for (int i = 0; i < count; i++)
+        for (int m = 0; m <= n; m++)
+            for (int k = 0; k < 7; k++) host[((size_t)i * (n + 1) + m) * MISA_ROW + k] = t[i].spline[(size_t)m * 7 + k];
+    cudaFree(*dptr);
+    *dptr = nullptr;
+    TRY(dmalloc(dptr, host.size()));
+    CU(cudaMemcpy(*dptr, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    *n_out = n;
+    *inv_out = t[0].inv_dx;
+    return MISA_B200_OK;
+}
+
+extern "C" int misa_b200_set_potential(misa_b200_ctx *c, int n_types, const misa_b200_table *elec,
+                                       const misa_b200_table *embed, const misa_b200_table *phi) {
+    REQ(c && elec && embed && phi && n_types >= 1 && n_types <= MISA_MAX_TYPES, MISA_B200_EINVAL,
+        "misa_b200_set_potential: bad argument");
+    DevTables &tb = c->tab;
+    tb.n_types = n_types;
+    int n_phi;
+    double inv_phi;
+    TRY(upload_tables(elec, n_types, &c->d_elec, &tb.n_r, &tb.inv_dr, "electron-density"));
+    TRY(upload_tables(embed, n_types, &c->d_embed, &tb.n_rho, &tb.inv_drho, "embedding"));
+    TRY(upload_tables(phi, n_types * n_types, &c->d_phi, &n_phi, &inv_phi, "pair"));
+    REQ(n_phi == tb.n_r && inv_phi == tb.inv_dr, MISA_B200_EINVAL,
+        "misa_b200_set_potential: pair and electron-density tables must share the r grid (setfl format)");
+    tb.elec = c->d_elec; tb.embed = c->d_embed; tb.phi = c->d_phi;
+    c->have_pot = true;
+    return MISA_B200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// transfers
+// -------------------------------------------------------------------------------------------------
+static int ensure_aos(misa_b200_ctx *c) {
+    if (!c->d_aos) TRY(dmalloc(&c->d_aos, (size_t)c->geo.n_ext * 104));
+    return 0;
+}
+static int h2d_aos(misa_b200_ctx *c, const void *atoms, int fields) {
+    TRY(ensure_aos(c));
+    CU(cudaMemcpyAsync(c->d_aos, atoms, (size_t)c->geo.n_ext * 104, cudaMemcpyHostToDevice, c->stream));
+    Slot sl(c, MISA_B200_K_XFER);
+    k_aos_to_soa<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->geo.H, (const unsigned long long *)c->d_aos, c->s, fields);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+static int d2h_aos(misa_b200_ctx *c, void *atoms, int fields, int owned_only) {
+    TRY(ensure_aos(c));
+    {
+        Slot sl(c, MISA_B200_K_XFER);
+        k_soa_to_aos<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo, (unsigned long long *)c->d_aos, c->s, fields, owned_only);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(atoms, c->d_aos, (size_t)c->geo.n_ext * 104, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int misa_b200_host_register(void *ptr, size_t bytes) {
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+extern "C" int misa_b200_host_unregister(void *ptr) {
+    CU(cudaHostUnregister(ptr));
+    return 0;
+}
+
+extern "C" int misa_b200_upload_atoms(misa_b200_ctx *c, const void *atoms) {
+    REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_upload_atoms: null argument");
+    TRY(h2d_aos(c, atoms, F_ALL));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_atoms = true;
+    c->invariant_ok = false;
+    return 0;
+}
+extern "C" int misa_b200_download_atoms(misa_b200_ctx *c, void *atoms) {
+    REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_download_atoms: null argument");
+    REQ(c->have_atoms, MISA_B200_ESTATE, "misa_b200_download_atoms: nothing uploaded");
+    // the staging copy may be stale or absent: rebuild every field from the SoA
+    TRY(ensure_aos(c));
+    CU(cudaMemsetAsync(c->d_aos, 0, (size_t)c->geo.n_ext * 104, c->stream));
+    return d2h_aos(c, atoms, F_ALL, 0);
+}
+
+extern "C" int misa_b200_sync(misa_b200_ctx *c) {
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int misa_b200_set_timestep(misa_b200_ctx *c, double dt) {
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    c->dt = dt; // NewtonMotion::preComputeDtInv2m, reference src/newton_motion.cpp:19-28
+    for (int i = 0; i < MISA_MAX_TYPES; i++) {
+        const double dt_halve = 0.5 * dt * kFtm2v;
+        c->dt_inv_m[i] = dt_halve / kMass[i];
+    }
+    return 0;
+}
+
+extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int value) {
+    REQ(c && name, MISA_B200_EINVAL, "null argument");
+    if (!strcmp(name, "prune")) c->opt_prune = value;
+    else if (!strcmp(name, "fuse")) c->opt_fuse = value;
+    else return fail(MISA_B200_EINVAL, std::string("unknown option ") + name);
+    return 0;
+}
+
+extern "C" int misa_b200_comm_unique_id(void *out128) {
+    REQ(out128, MISA_B200_EINVAL, "null argument");
+    TRY(nccl_load());
+    NC(g_nccl.GetUniqueId((nccl_uid *)out128));
+    return 0;
+}
+extern "C" int misa_b200_comm_init(misa_b200_ctx *c, const void *uid, int rank, int n_ranks) {
+    REQ(c && uid, MISA_B200_EINVAL, "null argument");
+    TRY(nccl_load());
+    nccl_uid id;
+    memcpy(&id, uid, sizeof id);
+    NC(g_nccl.CommInitRank(&c->nccl_comm, n_ranks, id, rank));
+    c->comm_rank = rank;
+    c->comm_size = n_ranks;
+    return 0;
+}
+extern "C" int misa_b200_comm_destroy(misa_b200_ctx *c) {
+    if (c && c->nccl_comm) {
+        g_nccl.CommDestroy(c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// halo exchange: comm::neiSendReceive<T> forward (x -> y -> z), restated on the device
+// -------------------------------------------------------------------------------------------------
+// width: doubles per site in the message (4 for positions+type, 1 for df)
+static int halo_forward(misa_b200_ctx *c, bool positions) {
+    const int width = positions ? 4 : 1;
+    if (c->all_self && c->n_ghost_map > 0) {
+        const int n = c->n_ghost_map;
+        if (positions)
+            k_ghost_fill_x<<<nblk(n), MISA_BLOCK, 0, c->stream>>>(n, c->d_ghost_dst, c->d_ghost_src, c->d_ghost_shift, c->s,
+                                                                 c->dom.meas_global_length[0], c->dom.meas_global_length[1],
+                                                                 c->dom.meas_global_length[2]);
+        else
+            k_ghost_fill_1<<<nblk(n), MISA_BLOCK, 0, c->stream>>>(n, c->d_ghost_dst, c->d_ghost_src, c->s.df);
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    for (int d = 0; d < 3; d++) {
+        const bool self = c->dom.grid_size[d] == 1;
+        if (self) {
+            for (int dir = 0; dir < 2; dir++) {
+                const HaloList &h = c->halo[d][dir];
+                if (positions)
+                    k_copy_x<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, h.d_recv, c->s, h.shift[0], h.shift[1], h.shift[2]);
+                else
+                    k_copy_1<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, h.d_recv, c->s.df);
+                c->launches++;
+            }
+            CU(cudaGetLastError());
+            continue;
+        }
+        REQ(c->nccl_comm, MISA_B200_ESTATE, "halo exchange across sub-boxes needs misa_b200_comm_init");
+        for (int dir = 0; dir < 2; dir++) {
+            const HaloList &h = c->halo[d][dir];
+            if (positions)
+                k_pack_x<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, c->s, h.shift[0], h.shift[1], h.shift[2], c->d_sendbuf[dir]);
+            else
+                k_pack_1<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, c->s.df, c->d_sendbuf[dir]);
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+        NC(g_nccl.GroupStart());
+        for (int dir = 0; dir < 2; dir++) {
+            const HaloList &h = c->halo[d][dir];
+            NC(g_nccl.Send(c->d_sendbuf[dir], (size_t)h.n * width, kNcclDouble, c->dom.rank_id_neighbours[d][dir], c->nccl_comm, c->stream));
+            NC(g_nccl.Recv(c->d_recvbuf[dir], (size_t)h.n * width, kNcclDouble, c->dom.rank_id_neighbours[d][(dir + 1) % 2], c->nccl_comm, c->stream));
+        }
+        NC(g_nccl.GroupEnd());
+        for (int dir = 0; dir < 2; dir++) {
+            const HaloList &h = c->halo[d][dir];
+            if (positions)
+                k_unpack_x<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_recv, c->s, c->d_recvbuf[dir]);
+            else
+                k_unpack_1<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_recv, c->s.df, c->d_recvbuf[dir]);
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// passes
+// -------------------------------------------------------------------------------------------------
+static int ready(misa_b200_ctx *c) {
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    REQ(c->have_off, MISA_B200_ESTATE, "neighbour offsets not set (cuda_nei_offset_init)");
+    REQ(c->have_pot, MISA_B200_ESTATE, "potential not set (cuda_pot_init)");
+    REQ(c->have_atoms, MISA_B200_ESTATE, "no atoms on the device");
+    return 0;
+}
+static inline bool use_pruned(const misa_b200_ctx *c) { return c->opt_prune && c->invariant_ok && c->n_pruned > 0; }
+static inline bool has_inter(const misa_b200_ctx *c) { return c->n_inter_local + c->n_inter_ghost > 0; }
+
+static int check_invariant(misa_b200_ctx *c) {
+    const Geo &g = c->geo;
+    const int bpp = nblk(g.n_cells_owned);
+    CU(cudaMemsetAsync(c->d_counters + 4, 0, sizeof(int), c->stream));
+    k_check_invariant<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, bpp, c->d_counters);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->invariant_ok = c->h_counters[4] == 0;
+    return 0;
+}
+
+extern "C" int misa_b200_pass_halo_x(misa_b200_ctx *c) {
+    TRY(ready(c));
+    Slot sl(c, MISA_B200_K_HALO_X);
+    return halo_forward(c, true);
+}
+extern "C" int misa_b200_pass_halo_df(misa_b200_ctx *c) {
+    TRY(ready(c));
+    {
+        Slot sl(c, MISA_B200_K_HALO_DF);
+        TRY(halo_forward(c, false));
+    }
+    if (c->inter_active) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_halo_df(c)); }
+    return 0;
+}
+extern "C" int misa_b200_pass_clear(misa_b200_ctx *c) {
+    TRY(ready(c));
+    k_clear<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->s.f[0], c->s.f[1], c->s.f[2], c->s.rho);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (has_inter(c)) TRY(inter_clear(c));
+    return 0;
+}
+
+static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
+    const Geo &g = c->geo;
+    const int bpp = nblk(g.n_cells_owned);
+    const bool pr = use_pruned(c);
+    const int *offs = pr ? c->d_off_pruned : c->d_off_full;
+    const int n_off = pr ? c->n_pruned : c->n_full;
+    const size_t sm = (size_t)n_off * sizeof(int);
+    Slot sl(c, MISA_B200_K_RHO);
+    if (accum) k_rho<false, true><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
+    else if (fuse_df) k_rho<true, false><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
+    else k_rho<false, false><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+static int launch_df(misa_b200_ctx *c) {
+    const int bpp = nblk(c->geo.n_cells_owned);
+    Slot sl(c, MISA_B200_K_DF);
+    k_df<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(c->geo, c->s, c->tab, bpp);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+static int launch_force(misa_b200_ctx *c, bool accum) {
+    const Geo &g = c->geo;
+    const int bpp = nblk(g.n_cells_owned);
+    const bool pr = use_pruned(c);
+    const int *offs = pr ? c->d_off_pruned : c->d_off_full;
+    const int n_off = pr ? c->n_pruned : c->n_full;
+    const size_t sm = (size_t)n_off * sizeof(int);
+    Slot sl(c, MISA_B200_K_FORCE);
+    if (accum) k_force<true><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
+    else k_force<false><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int misa_b200_pass_rho(misa_b200_ctx *c) {
+    TRY(ready(c));
+    TRY(launch_rho(c, false, false));
+    if (has_inter(c)) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_rho(c)); }
+    return 0;
+}
+extern "C" int misa_b200_pass_df(misa_b200_ctx *c) {
+    TRY(ready(c));
+    return launch_df(c);
+}
+extern "C" int misa_b200_pass_force(misa_b200_ctx *c) {
+    TRY(ready(c));
+    TRY(launch_force(c, false));
+    if (has_inter(c)) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_force(c)); }
+    return 0;
+}
+
+static VerletPar verlet_par(const misa_b200_ctx *c) {
+    VerletPar vp;
+    vp.dt = c->dt;
+    for (int i = 0; i < MISA_MAX_TYPES; i++) vp.c[i] = c->dt_inv_m[i];
+    return vp;
+}
+
+// Agree across all sub-boxes whether any off-lattice atom exists this step (the list exchanges are collective
+// between neighbours, so every rank must take the same branch); also brings the step counters to the host.
+static int update_activity(misa_b200_ctx *c) {
+    k_activity<<<1, 1, 0, c->stream>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost);
+    c->launches++;
+    if (c->comm_size > 1 && c->nccl_comm)
+        NC(g_nccl.AllReduce(c->d_counters + 8, c->d_counters + 9, 1, kNcclInt32, kNcclSum, c->nccl_comm, c->stream));
+    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, 10 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->inter_active = c->h_counters[9] > 0;
+    return 0;
+}
+
+// NewtonMotion::firststep + atom::decide (+ exchangeInter / borderInter when off-lattice atoms exist)
+extern "C" int misa_b200_pass_verlet1(misa_b200_ctx *c) {
+    TRY(ready(c));
+    const Geo &g = c->geo;
+    const int bpp = nblk(g.n_cells_owned);
+    const VerletPar vp = verlet_par(c);
+    if (c->n_inter_local > 0) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_first_step(c, vp)); }
+    {
+        Slot sl(c, MISA_B200_K_VERLET1);
+        CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
+        k_verlet1<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    TRY(update_activity(c));
+    REQ(c->h_counters[3] == 0, MISA_B200_EOVERFLOW, "run-away list overflow");
+    c->last_runaways = c->h_counters[0];
+    // every lattice atom that is still (or again) on a site after decide() may sit further than 0.2a from it
+    // when run-aways re-occupied sites: fall back to the full stencil for this step.
+    c->invariant_ok = c->last_runaways == 0;
+    if (c->inter_active) {
+        Slot sl(c, MISA_B200_K_INTER);
+        TRY(inter_decide(c, c->last_runaways));
+        TRY(inter_exchange(c));
+        TRY(inter_border(c));
+    } else {
+        inter_drop_ghosts(c);
+    }
+    return 0;
+}
+
+extern "C" int misa_b200_pass_verlet2(misa_b200_ctx *c) {
+    TRY(ready(c));
+    const int bpp = nblk(c->geo.n_cells_owned);
+    const VerletPar vp = verlet_par(c);
+    {
+        Slot sl(c, MISA_B200_K_VERLET2);
+        k_verlet2<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(c->geo, c->s, vp, bpp);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (c->n_inter_local > 0) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_second_step(c, vp)); }
+    return 0;
+}
+
+// atom::computeEam (reference src/atom.cpp:102-149) on the resident state. With the full-list gather the rho
+// and force reverse halos of the reference carry nothing and are omitted.
+static int compute_eam(misa_b200_ctx *c) {
+    const bool inter = has_inter(c);
+    if (inter) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_make_index(c)); }
+    const bool fuse = c->opt_fuse && !inter;
+    TRY(launch_rho(c, fuse, false));
+    if (inter) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_rho(c)); }
+    if (!fuse) TRY(launch_df(c));
+    TRY(misa_b200_pass_halo_df(c));
+    TRY(launch_force(c, false));
+    if (inter) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_force(c)); }
+    return 0;
+}
+
+extern "C" int misa_b200_prepare(misa_b200_ctx *c) {
+    TRY(ready(c));
+    TRY(misa_b200_pass_halo_x(c)); // exchangeAtomFirst: the lists are static, built in misa_b200_create
+    TRY(check_invariant(c));
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
+    TRY(update_activity(c));
+    if (c->inter_active) { TRY(inter_exchange(c)); TRY(inter_border(c)); }
+    TRY(misa_b200_pass_clear(c));
+    TRY(compute_eam(c));
+    return 0;
+}
+
+extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
+    TRY(ready(c));
+    for (int s = 0; s < n_steps; s++) {
+        TRY(misa_b200_pass_verlet1(c));
+        TRY(misa_b200_pass_halo_x(c));
+        // clearForce is folded into the stencil kernels' stores (owned sites are overwritten)
+        if (has_inter(c)) TRY(inter_clear(c));
+        TRY(compute_eam(c));
+        TRY(misa_b200_pass_verlet2(c));
+    }
+    return 0;
+}
+
+extern "C" int misa_b200_timed_steps(misa_b200_ctx *c, int n_steps, double *ms) {
+    TRY(ready(c));
+    REQ(ms, MISA_B200_EINVAL, "null argument");
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(e0, c->stream));
+    int rc = misa_b200_step(c, n_steps);
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms = f;
+    return rc;
+}
+
+// atom::setv, reference src/atom.cpp:475-494
+extern "C" int misa_b200_setv(misa_b200_ctx *c, const int32_t lat[4], const double direction[3], double energy) {
+    TRY(ready(c));
+    const Geo &g = c->geo;
+    const long long xl = 2LL * g.lo[0], yl = g.lo[1], zl = g.lo[2];
+    if ((lat[0] * 2) >= xl && (lat[0] * 2) < xl + 2LL * g.nx && lat[1] >= yl && lat[1] < yl + g.ny && lat[2] >= zl && lat[2] < zl + g.nz) {
+        const long long sx = 2LL * g.sxc;
+        const long long kk = ((lat[2] - (zl - g.gz)) * (long long)g.sy + (lat[1] - (yl - g.gy))) * sx + (lat[0] * 2 - (xl - 2LL * g.gx)) + lat[3];
+        const long long d = ref_to_dev(kk, g.H);
+        int8_t t;
+        double v[3];
+        CU(cudaMemcpyAsync(&t, c->s.type + d, 1, cudaMemcpyDeviceToHost, c->stream));
+        for (int k = 0; k < 3; k++) CU(cudaMemcpyAsync(&v[k], c->s.v[k] + d, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const double mass = t >= 0 ? kMass[t] : 0.0;
+        const double v_ = sqrt(2 * energy / mass / kMvv2e);
+        const double d_ = sqrt(direction[0] * direction[0] + direction[1] * direction[1] + direction[2] * direction[2]);
+        for (int k = 0; k < 3; k++) {
+            v[k] += v_ * direction[k] / d_;
+            CU(cudaMemcpyAsync(c->s.v[k] + d, &v[k], 8, cudaMemcpyHostToDevice, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// simulation::collisionStep, reference src/simulation.cpp:208-217
+extern "C" int misa_b200_collision_step(misa_b200_ctx *c, const int32_t lat[4], const double direction[3], double energy) {
+    TRY(misa_b200_setv(c, lat, direction, energy));
+    if (c->inter_active) { TRY(inter_exchange(c)); TRY(inter_border(c)); }
+    TRY(misa_b200_pass_halo_x(c));
+    TRY(misa_b200_pass_clear(c));
+    return compute_eam(c);
+}
+
+extern "C" int misa_b200_thermo(misa_b200_ctx *c, double out[6]) {
+    TRY(ready(c));
+    REQ(out, MISA_B200_EINVAL, "null argument");
+    const Geo &g = c->geo;
+    const int bpp = nblk(g.n_cells_owned);
+    CU(cudaMemsetAsync(c->d_reduce, 0, 8 * sizeof(double), c->stream));
+    k_thermo<<<2 * bpp, MISA_BLOCK, (size_t)c->n_full * sizeof(int), c->stream>>>(g, c->s, c->tab, c->d_off_full, c->n_full, bpp,
+                                                                                 kMass[0], kMass[1], kMass[2], c->d_reduce);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (c->n_inter_local > 0) TRY(inter_thermo(c, c->d_reduce));
+    CU(cudaMemcpyAsync(c->h_reduce, c->d_reduce, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out[0] = c->h_reduce[0];
+    out[1] = c->h_reduce[1];
+    out[2] = c->h_reduce[2];
+    out[3] = c->n_inter_local;
+    out[4] = c->n_inter_ghost;
+    out[5] = c->last_runaways;
+    return 0;
+}
+
+// configuration::rescale, reference src/system_configuration.cpp:86-111 (this rank's atoms; the caller
+// supplies the GLOBAL temperature factor through t_set / current T computed from all ranks' thermo[0]).
+extern "C" int misa_b200_rescale(misa_b200_ctx *c, double t_set, double t_now) {
+    TRY(ready(c));
+    REQ(t_now > 0, MISA_B200_EINVAL, "misa_b200_rescale: current temperature must be positive");
+    const double fac = sqrt(t_set / t_now);
+    k_scale_v<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->s.v[0], c->s.v[1], c->s.v[2], fac);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (c->n_inter_local > 0) TRY(inter_scale_v(c, fac));
+    (void)kBoltz;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// compat hooks on the HOST AoS array
+// -------------------------------------------------------------------------------------------------
+static int hook_common(misa_b200_ctx *c, void *atoms, double cutoff_radius) {
+    REQ(c && atoms, MISA_B200_EINVAL, "null argument");
+    REQ(c->have_off, MISA_B200_ESTATE, "neighbour offsets not set (cuda_nei_offset_init)");
+    REQ(c->have_pot, MISA_B200_ESTATE, "potential not set (cuda_pot_init)");
+    c->geo.rc2 = cutoff_radius * cutoff_radius; // reference src/atom.cpp:177
+    return 0;
+}
+
+extern "C" int misa_b200_eam_rho_calc(misa_b200_ctx *c, void *atoms, double cutoff_radius) {
+    TRY(hook_common(c, atoms, cutoff_radius));
+    TRY(h2d_aos(c, atoms, F_TYPE | F_X | F_RHO));
+    c->have_atoms = true;
+    TRY(check_invariant(c));
+    TRY(launch_rho(c, false, true));
+    return d2h_aos(c, atoms, F_RHO, 1);
+}
+extern "C" int misa_b200_eam_df_calc(misa_b200_ctx *c, void *atoms, double cutoff_radius) {
+    TRY(hook_common(c, atoms, cutoff_radius));
+    TRY(h2d_aos(c, atoms, F_TYPE | F_RHO));
+    c->have_atoms = true;
+    TRY(launch_df(c));
+    return d2h_aos(c, atoms, F_DF, 1);
+}
+extern "C" int misa_b200_eam_force_calc(misa_b200_ctx *c, void *atoms, double cutoff_radius) {
+    TRY(hook_common(c, atoms, cutoff_radius));
+    TRY(h2d_aos(c, atoms, F_TYPE | F_X | F_DF | F_F));
+    c->have_atoms = true;
+    TRY(check_invariant(c));
+    TRY(launch_force(c, true));
+    return d2h_aos(c, atoms, F_F, 1);
+}
+
+// -------------------------------------------------------------------------------------------------
+// inter-atom list transfer
+// -------------------------------------------------------------------------------------------------
+extern "C" int misa_b200_upload_inter(misa_b200_ctx *c, const void *inter_atoms, size_t n) {
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    return inter_upload(c, inter_atoms, n);
+}
+extern "C" int misa_b200_download_inter(misa_b200_ctx *c, void *inter_atoms, size_t cap, size_t *n) {
+    REQ(c && n, MISA_B200_EINVAL, "null argument");
+    return inter_download(c, inter_atoms, cap, n);
+}
+
+// -------------------------------------------------------------------------------------------------
+// profiling
+// -------------------------------------------------------------------------------------------------
+extern "C" int misa_b200_profile_enable(misa_b200_ctx *c, int on) {
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    c->prof_on = on != 0;
+    return 0;
+}
+extern "C" int misa_b200_profile_read(misa_b200_ctx *c, double ms_sum[MISA_B200_K_COUNT], int64_t launches[MISA_B200_K_COUNT]) {
+    REQ(c && ms_sum && launches, MISA_B200_EINVAL, "null argument");
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < MISA_B200_K_COUNT; k++) {
+        auto &ev = c->prof_ev[k];
+        for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+            float f = 0;
+            cudaEventElapsedTime(&f, ev[i], ev[i + 1]);
+            c->prof_ms[k] += f;
+            c->prof_n[k]++;
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        ms_sum[k] = c->prof_ms[k];
+        launches[k] = c->prof_n[k];
+        c->prof_ms[k] = 0;
+        c->prof_n[k] = 0;
+    }
+    return 0;
+}
+extern "C" int misa_b200_launch_count(misa_b200_ctx *c, int64_t *n) {
+    REQ(c && n, MISA_B200_EINVAL, "null argument");
+    *n = c->launches;
+    return 0;
+}

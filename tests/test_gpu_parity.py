@@ -1,0 +1,141 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs.
+Bars (BASELINE.json north_star): lattice indexing / occupancy / ownership bit-exact; per-atom rho, df, force
+within 1e-10 relative."""
+import numpy as np
+import pytest
+
+from tests import common as cm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def alloy_case():
+    st = cm.make_state((10, 11, 12), ratio=(90, 6, 4), sigma=0.05)
+    w = cm.oracle_world(st)
+    w.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    got = ctx.download()
+    yield st, w, ctx, got
+    ctx.close()
+    w.close()
+
+
+def test_halo_positions_bit_exact(alloy_case):
+    st, w, ctx, got = alloy_case
+    ref = w.atoms(0)
+    assert np.array_equal(got["type"], ref["type"])
+    assert np.array_equal(got["x"], ref["x"])  # ghosts carry the periodic image shift, bit-exact
+
+
+def test_rho_df_force_parity(alloy_case):
+    st, w, ctx, got = alloy_case
+    ref = cm.owned(ctx, w.atoms(0))
+    g = cm.owned(ctx, got)
+    assert cm.rel_err(g["rho"], ref["rho"]) < TOL
+    assert cm.rel_err(g["df"], ref["df"]) < TOL
+    assert cm.rel_err(g["f"], ref["f"]) < TOL
+    assert np.max(np.abs(ref["f"])) > 1e-2  # the test is not vacuous
+
+
+def test_pruned_and_full_stencil_agree(alloy_case):
+    st, w, ctx, got = alloy_case
+    ctx2 = cm.gpu_context(st)
+    ctx2.set_option("prune", 0)
+    ctx2.set_option("fuse", 0)
+    ctx2.prepare()
+    full = cm.owned(ctx2, ctx2.download())
+    g = cm.owned(ctx, got)
+    ctx2.close()
+    assert cm.rel_err(g["rho"], full["rho"]) < 1e-13
+    assert cm.rel_err(g["f"], full["f"]) < 1e-12
+
+
+def test_vacancies(alloy_case):
+    st = cm.make_state((8, 8, 8), ratio=(90, 6, 4), sigma=0.05, vacancies=40)
+    w = cm.oracle_world(st)
+    w.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    got = ctx.download()
+    ref = cm.owned(ctx, w.atoms(0))
+    g = cm.owned(ctx, got)
+    assert np.array_equal(g["type"], ref["type"])
+    valid = ref["type"] >= 0
+    assert cm.rel_err(g["rho"][valid], ref["rho"][valid]) < TOL
+    assert cm.rel_err(g["f"][valid], ref["f"][valid]) < TOL
+    assert np.all(g["rho"][~valid] == 0.0) and np.all(g["f"][~valid] == 0.0)
+    ctx.close()
+    w.close()
+
+
+def test_verlet_bit_exact():
+    """firststep / secondstep with identical forces must reproduce x and v to the last bit."""
+    st = cm.make_state((8, 9, 10), ratio=(90, 6, 4), sigma=0.05)
+    w = cm.oracle_world(st)
+    w.prepare()
+    ctx = cm.gpu_context(st, upload=False)
+    ctx.upload(w.atoms(0).copy())  # same f, v, x as the oracle
+    w.L.ora_first_step(w.h)
+    ctx.run_pass("verlet1")
+    got = cm.owned(ctx, ctx.download())
+    ref = cm.owned(ctx, w.atoms(0))
+    assert np.array_equal(got["x"], ref["x"])
+    assert np.array_equal(got["v"], ref["v"])
+    w.L.ora_second_step(w.h)
+    ctx.run_pass("verlet2")
+    got = cm.owned(ctx, ctx.download())
+    assert np.array_equal(got["v"], cm.owned(ctx, w.atoms(0))["v"])
+    ctx.close()
+    w.close()
+
+
+def test_ten_steps_track_oracle():
+    st = cm.make_state((10, 10, 10))
+    w = cm.oracle_world(st)
+    w.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    for _ in range(10):
+        w.step()
+    ctx.step(10)
+    got = cm.owned(ctx, ctx.download())
+    ref = cm.owned(ctx, w.atoms(0))
+    assert np.array_equal(got["type"], ref["type"])
+    assert cm.rel_err(got["x"], ref["x"]) < 1e-12
+    assert cm.rel_err(got["v"], ref["v"]) < 1e-9
+    assert cm.rel_err(got["f"], ref["f"]) < 1e-8
+    th = ctx.thermo()
+    assert abs(th["mvv"] - w.L.ora_mvv(w.h)) / th["mvv"] < 1e-10
+    assert abs(th["pe"] - w.potential_energy()) / abs(th["pe"]) < 1e-10
+    ctx.close()
+    w.close()
+
+
+def test_compat_hooks_match_cpu_branch():
+    """The three reference hooks on a HOST AoS array (ghosts already exchanged by the host) reproduce the
+    CPU branch of computeEam on owned sites."""
+    st = cm.make_state((8, 8, 9), ratio=(90, 6, 4), sigma=0.05)
+    w = cm.oracle_world(st)
+    w.L.ora_exchange_atom_first(w.h)
+    w.L.ora_clear_force(w.h)
+    host = w.atoms(0).copy()  # host array as the driver would hand it to the hooks
+    w.L.ora_compute_eam(w.h)
+    ref = w.atoms(0)
+    ctx = cm.gpu_context(st, upload=False)
+    ctx.eam_rho_calc(host)
+    own = ctx.owned
+    h3 = host.reshape(ctx.ext_shape)
+    r3 = ref.reshape(ctx.ext_shape)
+    assert cm.rel_err(h3[own]["rho"], r3[own]["rho"]) < TOL
+    ctx.eam_df_calc(host)
+    assert cm.rel_err(h3[own]["df"], r3[own]["df"]) < TOL
+    # the host's forward df halo (DfEmbedPacker) fills the ghosts before the force hook
+    h3["df"][...] = r3["df"]
+    ctx.eam_force_calc(host)
+    assert cm.rel_err(h3[own]["f"], r3[own]["f"]) < TOL
+    assert np.array_equal(host["x"], ref["x"]) and np.array_equal(host["id"], ref["id"])
+    ctx.close()
+    w.close()
