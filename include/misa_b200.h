@@ -118,6 +118,8 @@ int misa_b200_download_inter(misa_b200_ctx *ctx, void *inter_atoms, size_t cap, 
 int misa_b200_set_timestep(misa_b200_ctx *ctx, double dt);              /* NewtonMotion::setTimestepLength */
 int misa_b200_prepare(misa_b200_ctx *ctx);   /* exchangeAtomFirst + clearForce + computeEam (simulation.cpp:137-145) */
 int misa_b200_step(misa_b200_ctx *ctx, int n_steps); /* firststep .. secondstep, n times */
+/* the same loop body on a HOST AoS array: upload, n steps on the device, download (array coherent on return) */
+int misa_b200_step_host(misa_b200_ctx *ctx, void *atoms, int n_steps);
 int misa_b200_setv(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy); /* atom::setv */
 int misa_b200_collision_step(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy);
 int misa_b200_rescale(misa_b200_ctx *ctx, double t_set, double n_atoms_global); /* configuration::rescale (single rank sums; see thermo) */

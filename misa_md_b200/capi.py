@@ -24,7 +24,7 @@ EXPORTS = [
     "misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc",
     "misa_b200_host_register", "misa_b200_host_unregister",
     "misa_b200_upload_atoms", "misa_b200_download_atoms", "misa_b200_upload_inter", "misa_b200_download_inter",
-    "misa_b200_set_timestep", "misa_b200_prepare", "misa_b200_step", "misa_b200_setv", "misa_b200_collision_step",
+    "misa_b200_set_timestep", "misa_b200_prepare", "misa_b200_step", "misa_b200_step_host", "misa_b200_setv", "misa_b200_collision_step",
     "misa_b200_rescale", "misa_b200_thermo", "misa_b200_sync",
     "misa_b200_pass_halo_x", "misa_b200_pass_clear", "misa_b200_pass_rho", "misa_b200_pass_df", "misa_b200_pass_halo_df",
     "misa_b200_pass_force", "misa_b200_pass_verlet1", "misa_b200_pass_verlet2", "misa_b200_set_option",
@@ -88,6 +88,7 @@ def load(build=True):
     L.misa_b200_set_timestep.argtypes = [vp, d]
     L.misa_b200_prepare.argtypes = [vp]
     L.misa_b200_step.argtypes = [vp, i]
+    L.misa_b200_step_host.argtypes = [vp, vp, i]
     L.misa_b200_setv.argtypes = [vp, C.POINTER(C.c_int32 * 4), C.POINTER(d * 3), d]
     L.misa_b200_collision_step.argtypes = [vp, C.POINTER(C.c_int32 * 4), C.POINTER(d * 3), d]
     L.misa_b200_rescale.argtypes = [vp, d, d]
@@ -253,6 +254,10 @@ class Context:
 
     def step(self, n=1):
         _ck(self.L.misa_b200_step(self.h, n))
+
+    def step_host(self, atoms, n=1):
+        assert atoms.dtype == ATOM_DTYPE and atoms.size == self.n_ext and atoms.flags["C_CONTIGUOUS"]
+        _ck(self.L.misa_b200_step_host(self.h, atoms.ctypes.data, n))
 
     def timed_steps(self, n):
         ms = C.c_double()

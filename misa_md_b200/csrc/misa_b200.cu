@@ -729,6 +729,18 @@ extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
     return 0;
 }
 
+// Host-buffer form of the step loop: the AoS array the reference driver owns goes in, n steps run on the
+// device, and the array comes back coherent (every field of every site), so the unmodified host code around
+// the loop (dump, thermo, stage machine -- reference frontend/md_simulation.cpp:40-121) sees current data.
+extern "C" int misa_b200_step_host(misa_b200_ctx *c, void *atoms, int n_steps) {
+    REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_step_host: null argument");
+    REQ(c->have_off && c->have_pot, MISA_B200_ESTATE, "misa_b200_step_host: offsets / potential not set");
+    TRY(h2d_aos(c, atoms, F_ALL));
+    c->have_atoms = true;
+    TRY(misa_b200_step(c, n_steps));
+    return d2h_aos(c, atoms, F_ALL, 0);
+}
+
 extern "C" int misa_b200_timed_steps(misa_b200_ctx *c, int n_steps, double *ms) {
     TRY(ready(c));
     REQ(ms, MISA_B200_EINVAL, "null argument");

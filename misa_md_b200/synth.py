@@ -98,3 +98,27 @@ def perturb_positions(state, sigma, seed=7):
     rs = np.random.RandomState(seed)
     state["x"] = state["x"] + rs.normal(0.0, sigma, size=state["x"].shape)
     return state
+
+
+def create_sub_box_state(phase_space, grid, coord, a=2.85532, seed=466953, t_set=600.0, ratio=(1, 0, 0), crf=1.96125):
+    """Ghost-extended AoS array of ONE sub-box drawn the way the reference's WorldBuilder does it per rank:
+    every rank seeds the same generator and draws for its own owned sites (reference src/world_builder.cpp:
+    105-131), so the cost is O(sub-box), not O(global box). For identical sub-boxes the
+    global zero-momentum / rescale reductions equal the local ones. Used by bench.py for multi-GPU runs."""
+    lay = sub_box_layout(phase_space, grid, coord, crf)
+    n, lo = lay["n"], lay["lo"]
+    local = create_global_state(n, a=a, seed=seed, t_set=t_set, ratio=ratio)
+    px, py = int(phase_space[0]), int(phase_space[1])
+    k, j, i = np.meshgrid(np.arange(n[2]) + lo[2], np.arange(n[1]) + lo[1], np.arange(2 * n[0]) + 2 * lo[0], indexing="ij")
+    local["id"] = (1 + (k * py + j) * (2 * px) + i).astype(np.uint64)
+    x = local["x"]
+    x[..., 0] = i * 0.5 * a
+    x[..., 1] = j * a + (i % 2) * (a / 2)
+    x[..., 2] = k * a + (i % 2) * (a / 2)
+    arr = np.zeros(lay["ext_shape"], dtype=ATOM_DTYPE)
+    arr["type"] = INVALID
+    own = arr[lay["owned"]]
+    for fld in ("id", "type", "x", "v"):
+        own[fld] = local[fld]
+    arr[lay["owned"]] = own
+    return arr.reshape(-1), lay
