@@ -77,6 +77,15 @@ struct misa_b200_ctx {
     double *d_elec = nullptr, *d_embed = nullptr, *d_phi = nullptr;
     DevTables tab{};
     bool have_pot = false, have_off = false, have_atoms = false;
+    // Hermite (value, knot slope) copies of the r tables + the shared-memory staging plan (eam_smem.cuh)
+    double2 *d_herm = nullptr;            // [n_types + n_types^2][n_r + 1]
+    bool hermite_ok = false;              // caller's 7-coefficient rows are Hermite-consistent (checked on the host)
+    unsigned long long *d_census = nullptr, *h_census = nullptr; // valid sites per species (ghost-extended array)
+    unsigned long long census[MISA_MAX_TYPES] = {0, 0, 0};      // global (all sub-boxes) once prepare() ran
+    bool census_valid = false;
+    int sm_count = 0, smem_optin = 0;
+    int opt_smem = 1;                     // use the shared-memory table kernels when possible
+    double stage_r_lo = 2.0;              // tables are staged for r >= stage_r_lo (Angstrom)
     // halo
     HaloList halo[3][2];
     bool all_self = true;                 // 1x1x1 grid: every neighbour is this sub-box

@@ -1,0 +1,280 @@
+// misa_md_b200/csrc/eam_smem.cuh -- the production rho / force kernels: spline tables staged in shared
+// memory by TMA bulk copies, persistent CTAs (one per SM), warp = 32 consecutive owned cells of ONE sub-lattice.
+//
+// Why (profiles/r01a_ncu_full_summary.csv): with the 7-coefficient rows in global memory both stencil kernels
+// sit at 98 % of the L1 LSU wavefront limit (every pair gathers 2-3 rows of 64 B from 32 different lines per
+// warp instruction) while the fp64 pipe idles at 13-17 %. Here the tables live in shared memory in HERMITE
+// form -- one double2 (value, knot slope) per knot, i.e. columns 6 and 5 of the reference's 7-coefficient row
+// (libpot InterpolationObject / LAMMPS array2spline, restated in oracle/pot.c:table_build) -- and the two cubic
+// coefficients are rebuilt in registers with the formulas of table_build:
+//     s4 = 3 (v1 - v0) - 2 d0 - d1,   s3 = d0 + d1 - 2 (v1 - v0),
+//     value = ((s3 p + s4) p + d0) p + v0,   derivative = ((3 s3 p + 2 s4) p + d0) / dx.
+// A pair then costs 2 LDS.128 per table instead of 7 scattered LDG.64, and 16 B per knot lets the r-range a
+// solid ever visits ([r_lo, r_c], about 3200 knots) fit in 51 KB per table. Rows below r_lo (close cascade
+// encounters) and tables that are not staged are read from the global Hermite copies -- same arithmetic.
+// set_potential() verifies on the host that the caller's 7-coefficient rows ARE the Hermite-consistent ones;
+// if not, the generic global-table kernels in kernels.cuh are used instead.
+//
+// Deviations from the reference's operation order (all far below the 1e-10 parity bar):
+// r = d2 * rsqrt(d2) instead of sqrt(d2); 1/r = rsqrt(d2); the derivative multiplies by 1/dx.
+#pragma once
+#include "ctx.h"
+#include "kernels.cuh"
+
+#define EAM_THREADS 1024
+#define EAM_MAX_STAGED 4
+
+struct StagePlan {
+    // global Hermite copies, always present: elec[t] and phi[ti * n_types + tj], each (n_r + 1) double2
+    const double2 *g_elec[MISA_MAX_TYPES];
+    const double2 *g_phi[MISA_MAX_TYPES * MISA_MAX_TYPES];
+    int n_staged;                       // tables copied to shared memory by this launch
+    int staged_id[EAM_MAX_STAGED];      // < MISA_MAX_TYPES: elec[id]; else phi[id - MISA_MAX_TYPES]
+    int row_lo;                         // first staged row
+    int rows_s;                         // staged rows per table (row_lo .. n_r)
+    int off_bytes;                      // byte offset of the table area inside dynamic smem (after the offsets)
+    int single;                         // >= 0: every valid site has this type (single-species fast path)
+};
+
+// ---- TMA / mbarrier plumbing (1-D bulk copies; SASS: UBLKCP) -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(smem_u32(b)), "r"(phase)
+                     : "memory");
+    } while (!ok);
+}
+
+// Stage the planned tables and the neighbour offsets; returns the shared-memory table area.
+__device__ __forceinline__ double2 *stage_tables(const StagePlan &sp, unsigned char *smem, uint64_t *mbar, const int *__restrict__ offs,
+                                                 const int n_off2) {
+    int *s_off = reinterpret_cast<int *>(smem);
+    double2 *s_tab = reinterpret_cast<double2 *>(smem + sp.off_bytes);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    for (int q = threadIdx.x; q < n_off2; q += blockDim.x) s_off[q] = offs[q];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)sp.rows_s * 16u;
+        mbar_expect_tx(mbar, bytes * (uint32_t)sp.n_staged);
+        for (int k = 0; k < sp.n_staged; k++) {
+            const int id = sp.staged_id[k];
+            const double2 *src = (id < MISA_MAX_TYPES ? sp.g_elec[id] : sp.g_phi[id - MISA_MAX_TYPES]) + sp.row_lo;
+            unsigned char *dst = reinterpret_cast<unsigned char *>(s_tab + (size_t)k * sp.rows_s);
+            for (uint32_t o = 0; o < bytes; o += 32768u)
+                tma_load_1d(dst + o, reinterpret_cast<const unsigned char *>(src) + o, min(32768u, bytes - o), mbar);
+        }
+    }
+    mbar_wait(mbar, 0);
+    return s_tab;
+}
+
+// ---- spline helpers ------------------------------------------------------------------------------------
+// libpot findSpline (oracle/pot.c:table_find): p = x*inv_dx + 1; m = clamp(int(p), 1, n-1); p = min(p - m, 1).
+// int(p) is taken with a round-down add of 2^52 (p > 0): no F2I / I2F on the XU pipe.
+__device__ __forceinline__ int split_index(const double x, const double inv_dx, const int n, double &frac) {
+    const double pp = fma(x, inv_dx, 1.0);
+    const double t = __dadd_rd(pp, 4503599627370496.0);
+    int m = __double2loint(t);
+    double mf = t - 4503599627370496.0;
+    if (m > n - 1 || m < 1) { // off the table: clamp like the reference
+        m = max(1, min(m, n - 1));
+        mf = (double)m;
+    }
+    frac = fmin(pp - mf, 1.0);
+    return m;
+}
+struct Cubic { double s3, s4, d0, v0; };
+__device__ __forceinline__ Cubic hermite(const double2 a, const double2 b) {
+    const double dv = b.x - a.x;
+    Cubic c;
+    c.s4 = 3.0 * dv - 2.0 * a.y - b.y;
+    c.s3 = a.y + b.y - 2.0 * dv;
+    c.d0 = a.y;
+    c.v0 = a.x;
+    return c;
+}
+__device__ __forceinline__ double cubic_value(const Cubic &c, const double p) { return ((c.s3 * p + c.s4) * p + c.d0) * p + c.v0; }
+// derivative w.r.t. p (multiply by 1/dx for d/dx)
+__device__ __forceinline__ double cubic_slope(const Cubic &c, const double p) { return (3.0 * c.s3 * p + 2.0 * c.s4) * p + c.d0; }
+
+// row pair (m, m+1) of a table: shared copy when staged and m >= row_lo, else the global Hermite copy
+__device__ __forceinline__ Cubic fetch_cubic(const double2 *__restrict__ s_rows /* biased by -row_lo, or nullptr */,
+                                             const double2 *__restrict__ g_rows, const int row_lo, const int m) {
+    if (s_rows != nullptr && m >= row_lo) return hermite(s_rows[m], s_rows[m + 1]);
+    return hermite(__ldg(g_rows + m), __ldg(g_rows + m + 1));
+}
+
+// per-CTA table directory in shared memory (multi-species path): pointers biased by -row_lo, nullptr if not staged
+struct TabDir {
+    const double2 *s_elec[MISA_MAX_TYPES];
+    const double2 *s_phi[MISA_MAX_TYPES * MISA_MAX_TYPES];
+};
+__device__ __forceinline__ void build_dir(TabDir *dir, const StagePlan &sp, const double2 *s_tab) {
+    if (threadIdx.x < MISA_MAX_TYPES) dir->s_elec[threadIdx.x] = nullptr;
+    if (threadIdx.x < MISA_MAX_TYPES * MISA_MAX_TYPES) dir->s_phi[threadIdx.x] = nullptr;
+    __syncthreads();
+    if (threadIdx.x < sp.n_staged) {
+        const int id = sp.staged_id[threadIdx.x];
+        const double2 *p = s_tab + (size_t)threadIdx.x * sp.rows_s - sp.row_lo;
+        if (id < MISA_MAX_TYPES) dir->s_elec[id] = p;
+        else dir->s_phi[id - MISA_MAX_TYPES] = p;
+    }
+    __syncthreads();
+}
+
+// warp work unit u -> owned cell of this lane (or -1)
+__device__ __forceinline__ int unit_to_dev(const Geo &g, const long long u, const long long units_per_parity, const int lane) {
+    const int p = u >= units_per_parity;
+    const long long c = (u - (long long)p * units_per_parity) * 32 + lane;
+    if (c >= g.n_cells_owned) return -1;
+    int cx, y, z;
+    return owned_cell_to_dev(g, p, c, cx, y, z);
+}
+
+// ---- K1 rho (+ K2 df fused): atom::latRho / latDf (reference src/atom.cpp:151-192,286-309), full-list gather ----
+// SINGLE: every valid site has type sp.single and tables 0 (elec) / 1 (phi) of the staging area are its own.
+template <bool SINGLE, bool FUSE_DF, bool ACCUM>
+__global__ void __launch_bounds__(EAM_THREADS, 1)
+k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    __shared__ TabDir dir;
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
+    if (!SINGLE) build_dir(&dir, sp, s_tab);
+    const int *s_off = reinterpret_cast<const int *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
+    const long long upp = (g.n_cells_owned + 31) / 32;
+    const double2 *s_el0 = s_tab - sp.row_lo; // SINGLE: staged slot 0 = elec[single]
+    const double2 *g_el0 = sp.g_elec[SINGLE ? sp.single : 0];
+    for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
+        const int d = unit_to_dev(g, u, upp, lane);
+        if (d < 0) continue;
+        const int ti = s.type[d];
+        if (ti < 0) {
+            if (!ACCUM) s.rho[d] = 0.0;
+            continue;
+        }
+        const int *off = s_off + (u >= upp ? n_off : 0);
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+        double acc = 0.0;
+#pragma unroll 2
+        for (int q = 0; q < n_off; q++) {
+            const int j = d + off[q];
+            const int tj = s.type[j];
+            const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (tj >= 0 && d2 < g.rc2) {
+                const double r = d2 * rsqrt(d2);
+                double p;
+                const int m = split_index(r, tb.inv_dr, tb.n_r, p);
+                const Cubic c = SINGLE ? fetch_cubic(s_el0, g_el0, sp.row_lo, m) : fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
+                acc += cubic_value(c, p);
+            }
+        }
+        if (ACCUM) acc += s.rho[d];
+        s.rho[d] = acc;
+        if (FUSE_DF) s.df[d] = d_embed(tb, ti, acc);
+    }
+}
+
+// ---- K3 force: atom::latForce (reference src/atom.cpp:311-358), full-list gather ---------------------------
+template <bool SINGLE, bool ACCUM>
+__global__ void __launch_bounds__(EAM_THREADS, 1)
+k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    __shared__ TabDir dir;
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
+    if (!SINGLE) build_dir(&dir, sp, s_tab);
+    const int *s_off = reinterpret_cast<const int *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
+    const long long upp = (g.n_cells_owned + 31) / 32;
+    const int nt = tb.n_types;
+    const double2 *s_el0 = s_tab - sp.row_lo;                       // SINGLE: slot 0 = elec[single]
+    const double2 *s_ph0 = s_tab + (size_t)sp.rows_s - sp.row_lo;   // SINGLE: slot 1 = phi[single][single]
+    const double2 *g_el0 = sp.g_elec[SINGLE ? sp.single : 0];
+    const double2 *g_ph0 = sp.g_phi[SINGLE ? sp.single * nt + sp.single : 0];
+    for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
+        const int d = unit_to_dev(g, u, upp, lane);
+        if (d < 0) continue;
+        const int ti = s.type[d];
+        if (ti < 0) {
+            if (!ACCUM) { s.f[0][d] = 0.0; s.f[1][d] = 0.0; s.f[2][d] = 0.0; }
+            continue;
+        }
+        const int *off = s_off + (u >= upp ? n_off : 0);
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+        const double dfi = s.df[d];
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+#pragma unroll 2
+        for (int q = 0; q < n_off; q++) {
+            const int j = d + off[q];
+            const int tj = s.type[j];
+            const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (tj >= 0 && d2 < g.rc2) {
+                const double recip = rsqrt(d2);
+                const double r = d2 * recip;
+                const double dfj = s.df[j];
+                double p;
+                const int m = split_index(r, tb.inv_dr, tb.n_r, p);
+                double z2, z2p, emb;
+                if (SINGLE) {
+                    const Cubic cp = fetch_cubic(s_ph0, g_ph0, sp.row_lo, m);
+                    const Cubic ce = fetch_cubic(s_el0, g_el0, sp.row_lo, m);
+                    z2 = cubic_value(cp, p);
+                    z2p = cubic_slope(cp, p) * tb.inv_dr;
+                    const double rho_p = cubic_slope(ce, p) * tb.inv_dr;
+                    emb = rho_p * dfj + rho_p * dfi;
+                } else {
+                    const Cubic cp = fetch_cubic(dir.s_phi[ti * nt + tj], sp.g_phi[ti * nt + tj], sp.row_lo, m);
+                    const Cubic ci = fetch_cubic(dir.s_elec[ti], sp.g_elec[ti], sp.row_lo, m);
+                    z2 = cubic_value(cp, p);
+                    z2p = cubic_slope(cp, p) * tb.inv_dr;
+                    const double rho_p_from = cubic_slope(ci, p) * tb.inv_dr;
+                    double rho_p_to = rho_p_from;
+                    if (tj != ti) {
+                        const Cubic cj = fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
+                        rho_p_to = cubic_slope(cj, p) * tb.inv_dr;
+                    }
+                    emb = rho_p_from * dfj + rho_p_to * dfi;
+                }
+                // eam::toForce (oracle/pot.c:pot_to_force): phi = z2/r, phi' = z2'/r - phi/r, fpair = -(phi' + emb)/r
+                const double phi = z2 * recip;
+                const double phip = z2p * recip - phi * recip;
+                const double fp = -(phip + emb) * recip;
+                fx += dx * fp; fy += dy * fp; fz += dz * fp;
+            }
+        }
+        if (ACCUM) { fx += s.f[0][d]; fy += s.f[1][d]; fz += s.f[2][d]; }
+        s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz;
+    }
+}
+
+// ---- species census (decides SINGLE vs multi and what to stage) ------------------------------------------
+__global__ void __launch_bounds__(MISA_BLOCK) k_census(const long long n, const int8_t *__restrict__ type, unsigned long long *__restrict__ count) {
+    __shared__ unsigned int sh[MISA_MAX_TYPES];
+    if (threadIdx.x < MISA_MAX_TYPES) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = type[i];
+        if (t >= 0 && t < MISA_MAX_TYPES) atomicAdd(&sh[t], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < MISA_MAX_TYPES && sh[threadIdx.x]) atomicAdd(&count[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "nccl_dl.cuh"
 #include "inter.cuh"
+#include "eam_smem.cuh"
 
 extern "C" const char *misa_b200_last_error(void) { return g_err.c_str(); }
 
@@ -78,6 +79,24 @@ struct Slot {
 };
 
 static inline int nblk(long long n) { return (int)((n + MISA_BLOCK - 1) / MISA_BLOCK); }
+
+// -------------------------------------------------------------------------------------------------
+// shared-memory table kernels (eam_smem.cuh): opt in to the large dynamic shared memory once
+// -------------------------------------------------------------------------------------------------
+static int census_local(misa_b200_ctx *c);
+static int census_fetch(misa_b200_ctx *c);
+static int smem_kernels_init(int optin) {
+    static bool done = false;
+    if (done) return 0;
+#define OPTIN(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)) /* static smem: mbarrier + table directory */
+    OPTIN((k_rho_s<true, true, false>)); OPTIN((k_rho_s<true, false, false>)); OPTIN((k_rho_s<true, false, true>));
+    OPTIN((k_rho_s<false, true, false>)); OPTIN((k_rho_s<false, false, false>)); OPTIN((k_rho_s<false, false, true>));
+    OPTIN((k_force_s<true, false>)); OPTIN((k_force_s<true, true>));
+    OPTIN((k_force_s<false, false>)); OPTIN((k_force_s<false, true>));
+#undef OPTIN
+    done = true;
+    return 0;
+}
 
 // -------------------------------------------------------------------------------------------------
 // create / destroy
@@ -196,6 +215,11 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
         CU(cudaMemcpy(c->d_ghost_shift, codes.data(), codes.size(), cudaMemcpyHostToDevice));
     }
     TRY(inter_alloc(c, 1 << 16));
+    TRY(dmalloc(&c->d_census, MISA_MAX_TYPES));
+    CU(cudaMallocHost((void **)&c->h_census, MISA_MAX_TYPES * sizeof(unsigned long long)));
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    CU(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    TRY(smem_kernels_init(c->smem_optin));
     misa_b200_set_timestep(c, 0.001);
     *out = c;
     return MISA_B200_OK;
@@ -208,7 +232,8 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int k = 0; k < 3; k++) { cudaFree(c->s.x[k]); cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
     cudaFree(c->s.rho); cudaFree(c->s.df); cudaFree(c->s.type); cudaFree(c->s.id);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_pruned);
-    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi);
+    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
+    cudaFree(c->d_census); cudaFreeHost(c->h_census);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
@@ -338,6 +363,40 @@ static int upload_tables(const misa_b200_table *t, int count, double **dptr, int
     return MISA_B200_OK;
 }
 
+// Hermite copies (value, knot slope) = columns 6 and 5 of every r-table row, and the host-side proof that the
+// caller's rows are what eam_smem.cuh rebuilds from them: s4 = 3dv - 2d0 - d1, s3 = d0 + d1 - 2dv (rows 1..n-1),
+// s2 = s5/dx, s1 = 2 s4/dx, s0 = 3 s3/dx (oracle/pot.c:table_build / LAMMPS array2spline).
+static int build_hermite(misa_b200_ctx *c, const misa_b200_table *elec, const misa_b200_table *phi) {
+    const int nt = c->tab.n_types, n = c->tab.n_r, ntab = nt + nt * nt;
+    std::vector<double> h((size_t)ntab * (n + 1) * 2, 0.0);
+    bool ok = true;
+    for (int t = 0; t < ntab; t++) {
+        const double *sp = (t < nt ? elec[t] : phi[t - nt]).spline;
+        const double inv_dx = c->tab.inv_dr;
+        double scale = 0.0;
+        for (int m = 1; m <= n; m++) scale = std::max(scale, fabs(sp[(size_t)m * 7 + 6]));
+        const double tol = 1e-12 * std::max(scale, 1e-300);
+        for (int m = 0; m <= n; m++) {
+            h[((size_t)t * (n + 1) + m) * 2 + 0] = sp[(size_t)m * 7 + 6];
+            h[((size_t)t * (n + 1) + m) * 2 + 1] = sp[(size_t)m * 7 + 5];
+        }
+        for (int m = 1; m <= n - 1 && ok; m++) {
+            const double *a = sp + (size_t)m * 7, *b = a + 7;
+            const double dv = b[6] - a[6];
+            const double s4 = 3.0 * dv - 2.0 * a[5] - b[5], s3 = a[5] + b[5] - 2.0 * dv;
+            if (fabs(s4 - a[4]) > tol || fabs(s3 - a[3]) > tol || fabs(a[2] - a[5] * inv_dx) > tol * inv_dx ||
+                fabs(a[1] - 2.0 * a[4] * inv_dx) > tol * inv_dx || fabs(a[0] - 3.0 * a[3] * inv_dx) > tol * inv_dx)
+                ok = false;
+        }
+    }
+    cudaFree(c->d_herm);
+    c->d_herm = nullptr;
+    TRY(dmalloc(&c->d_herm, h.size() / 2));
+    CU(cudaMemcpy(c->d_herm, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->hermite_ok = ok;
+    return 0;
+}
+
 extern "C" int misa_b200_set_potential(misa_b200_ctx *c, int n_types, const misa_b200_table *elec,
                                        const misa_b200_table *embed, const misa_b200_table *phi) {
     REQ(c && elec && embed && phi && n_types >= 1 && n_types <= MISA_MAX_TYPES, MISA_B200_EINVAL,
@@ -352,6 +411,7 @@ extern "C" int misa_b200_set_potential(misa_b200_ctx *c, int n_types, const misa
     REQ(n_phi == tb.n_r && inv_phi == tb.inv_dr, MISA_B200_EINVAL,
         "misa_b200_set_potential: pair and electron-density tables must share the r grid (setfl format)");
     tb.elec = c->d_elec; tb.embed = c->d_embed; tb.phi = c->d_phi;
+    TRY(build_hermite(c, elec, phi));
     c->have_pot = true;
     return MISA_B200_OK;
 }
@@ -397,7 +457,8 @@ extern "C" int misa_b200_host_unregister(void *ptr) {
 extern "C" int misa_b200_upload_atoms(misa_b200_ctx *c, const void *atoms) {
     REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_upload_atoms: null argument");
     TRY(h2d_aos(c, atoms, F_ALL));
-    CU(cudaStreamSynchronize(c->stream));
+    TRY(census_local(c));
+    TRY(census_fetch(c));
     c->have_atoms = true;
     c->invariant_ok = false;
     return 0;
@@ -431,6 +492,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     REQ(c && name, MISA_B200_EINVAL, "null argument");
     if (!strcmp(name, "prune")) c->opt_prune = value;
     else if (!strcmp(name, "fuse")) c->opt_fuse = value;
+    else if (!strcmp(name, "smem")) c->opt_smem = value;
     else return fail(MISA_B200_EINVAL, std::string("unknown option ") + name);
     return 0;
 }
@@ -569,6 +631,48 @@ extern "C" int misa_b200_pass_clear(misa_b200_ctx *c) {
     return 0;
 }
 
+// Species census of the ghost-extended array. The set of species is an invariant of a run (atoms are neither
+// created nor transmuted), so resident mode takes it once (upload + prepare, summed over sub-boxes); the compat
+// hooks take it on every call because the host owns the array between calls.
+static int census_local(misa_b200_ctx *c) {
+    CU(cudaMemsetAsync(c->d_census, 0, MISA_MAX_TYPES * sizeof(unsigned long long), c->stream));
+    k_census<<<std::min(nblk(c->geo.n_ext), 4 * std::max(c->sm_count, 1)), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->s.type, c->d_census);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+static int census_fetch(misa_b200_ctx *c) {
+    CU(cudaMemcpyAsync(c->h_census, c->d_census, MISA_MAX_TYPES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < MISA_MAX_TYPES; t++) c->census[t] = c->h_census[t];
+    c->census_valid = true;
+    return 0;
+}
+
+// What the stencil kernels stage in shared memory: the majority species' elec and phi tables for r >= r_lo.
+static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes) {
+    if (!c->opt_smem || !c->hermite_ok || !c->census_valid || c->sm_count <= 0) return false;
+    const int nt = c->tab.n_types, n = c->tab.n_r;
+    int present = 0, maj = 0;
+    for (int t = 0; t < MISA_MAX_TYPES; t++) {
+        if (c->census[t] && t >= nt) return false; // a species the potential does not cover
+        if (c->census[t]) present++;
+        if (c->census[t] > c->census[maj]) maj = t;
+    }
+    memset(&sp, 0, sizeof sp);
+    for (int t = 0; t < nt; t++) sp.g_elec[t] = c->d_herm + (size_t)t * (n + 1);
+    for (int t = 0; t < nt * nt; t++) sp.g_phi[t] = c->d_herm + (size_t)(nt + t) * (n + 1);
+    sp.single = present <= 1 ? maj : -1;
+    sp.row_lo = std::max(1, std::min(n - 2, (int)(c->stage_r_lo * c->tab.inv_dr) - 1));
+    sp.rows_s = n + 1 - sp.row_lo;
+    sp.off_bytes = (int)((2 * (size_t)c->n_full * sizeof(int) + 127) / 128 * 128);
+    sp.n_staged = 2;
+    sp.staged_id[0] = maj;                              // elec[maj]
+    sp.staged_id[1] = MISA_MAX_TYPES + maj * nt + maj;  // phi[maj][maj]
+    smem_bytes = (size_t)sp.off_bytes + (size_t)sp.n_staged * sp.rows_s * 16;
+    return smem_bytes + 1024 <= (size_t)c->smem_optin;
+}
+
 static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
@@ -577,6 +681,18 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
     const int n_off = pr ? c->n_pruned : c->n_full;
     const size_t sm = (size_t)n_off * sizeof(int);
     Slot sl(c, MISA_B200_K_RHO);
+    StagePlan sp;
+    size_t sb;
+    if (make_plan(c, sp, sb)) {
+        const int grid = c->sm_count;
+#define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off)
+        if (sp.single >= 0) { if (accum) RHO_S(true, false, true); else if (fuse_df) RHO_S(true, true, false); else RHO_S(true, false, false); }
+        else { if (accum) RHO_S(false, false, true); else if (fuse_df) RHO_S(false, true, false); else RHO_S(false, false, false); }
+#undef RHO_S
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (accum) k_rho<false, true><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
     else if (fuse_df) k_rho<true, false><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
     else k_rho<false, false><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
@@ -600,6 +716,18 @@ static int launch_force(misa_b200_ctx *c, bool accum) {
     const int n_off = pr ? c->n_pruned : c->n_full;
     const size_t sm = (size_t)n_off * sizeof(int);
     Slot sl(c, MISA_B200_K_FORCE);
+    StagePlan sp;
+    size_t sb;
+    if (make_plan(c, sp, sb)) {
+        const int grid = c->sm_count;
+#define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off)
+        if (sp.single >= 0) { if (accum) FORCE_S(true, true); else FORCE_S(true, false); }
+        else { if (accum) FORCE_S(false, true); else FORCE_S(false, false); }
+#undef FORCE_S
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (accum) k_force<true><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
     else k_force<false><<<2 * bpp, MISA_BLOCK, sm, c->stream>>>(g, c->s, c->tab, offs, n_off, bpp);
     c->launches++;
@@ -707,6 +835,10 @@ static int compute_eam(misa_b200_ctx *c) {
 extern "C" int misa_b200_prepare(misa_b200_ctx *c) {
     TRY(ready(c));
     TRY(misa_b200_pass_halo_x(c)); // exchangeAtomFirst: the lists are static, built in misa_b200_create
+    TRY(census_local(c));          // ghosts are filled now; sum over sub-boxes so every rank plans alike
+    if (c->comm_size > 1 && c->nccl_comm)
+        NC(g_nccl.AllReduce(c->d_census, c->d_census, MISA_MAX_TYPES, kNcclUint64, kNcclSum, c->nccl_comm, c->stream));
+    TRY(census_fetch(c));
     TRY(check_invariant(c));
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
     TRY(update_activity(c));
@@ -736,6 +868,7 @@ extern "C" int misa_b200_step_host(misa_b200_ctx *c, void *atoms, int n_steps) {
     REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_step_host: null argument");
     REQ(c->have_off && c->have_pot, MISA_B200_ESTATE, "misa_b200_step_host: offsets / potential not set");
     TRY(h2d_aos(c, atoms, F_ALL));
+    if (!c->census_valid) { TRY(census_local(c)); TRY(census_fetch(c)); }
     c->have_atoms = true;
     TRY(misa_b200_step(c, n_steps));
     return d2h_aos(c, atoms, F_ALL, 0);
@@ -844,6 +977,8 @@ extern "C" int misa_b200_eam_rho_calc(misa_b200_ctx *c, void *atoms, double cuto
     TRY(hook_common(c, atoms, cutoff_radius));
     TRY(h2d_aos(c, atoms, F_TYPE | F_X | F_RHO));
     c->have_atoms = true;
+    TRY(census_local(c));
+    TRY(census_fetch(c));
     TRY(check_invariant(c));
     TRY(launch_rho(c, false, true));
     return d2h_aos(c, atoms, F_RHO, 1);
@@ -859,6 +994,8 @@ extern "C" int misa_b200_eam_force_calc(misa_b200_ctx *c, void *atoms, double cu
     TRY(hook_common(c, atoms, cutoff_radius));
     TRY(h2d_aos(c, atoms, F_TYPE | F_X | F_DF | F_F));
     c->have_atoms = true;
+    TRY(census_local(c));
+    TRY(census_fetch(c));
     TRY(check_invariant(c));
     TRY(launch_force(c, true));
     return d2h_aos(c, atoms, F_F, 1);

@@ -53,6 +53,48 @@ def test_pruned_and_full_stencil_agree(alloy_case):
     assert cm.rel_err(g["f"], full["f"]) < 1e-12
 
 
+@pytest.mark.parametrize("ratio", [(1, 0, 0), (0, 1, 0), (90, 6, 4)])
+def test_smem_tables_match_generic_tables(ratio):
+    """eam_smem.cuh (Hermite tables staged in shared memory by TMA) vs kernels.cuh (7-coefficient rows in global
+    memory, the reference's evaluation order) -- both against the oracle, single- and multi-species."""
+    st = cm.make_state((9, 10, 11), ratio=ratio, sigma=0.06)
+    w = cm.oracle_world(st)
+    w.prepare()
+    ref = None
+    out = {}
+    for smem in (1, 0):
+        ctx = cm.gpu_context(st)
+        ctx.set_option("smem", smem)
+        ctx.prepare()
+        out[smem] = cm.owned(ctx, ctx.download())
+        ref = cm.owned(ctx, w.atoms(0))
+        ctx.close()
+    w.close()
+    for smem in (1, 0):
+        for fld in ("rho", "df", "f"):
+            assert cm.rel_err(out[smem][fld], ref[fld]) < TOL, (smem, fld)
+    assert cm.rel_err(out[1]["f"], out[0]["f"]) < 1e-11
+
+
+def test_close_pairs_below_staged_range():
+    """Pairs closer than the staged r range (r < 2 Angstrom) take the global Hermite rows: same results."""
+    st = cm.make_state((8, 8, 8), sigma=0.0)
+    x = st["x"]
+    x[4, 4, 8] += (x[4, 4, 9] - x[4, 4, 8]) * 0.22  # push one atom towards its 1nn: r ~ 1.93 A, still < 0.2a... from its site
+    w = cm.oracle_world(st)
+    w.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    got = cm.owned(ctx, ctx.download())
+    ref = cm.owned(ctx, w.atoms(0))
+    d = np.linalg.norm(st["x"][4, 4, 9] - st["x"][4, 4, 8])
+    assert d < 2.0
+    for fld in ("rho", "df", "f"):
+        assert cm.rel_err(got[fld], ref[fld]) < TOL, fld
+    ctx.close()
+    w.close()
+
+
 def test_vacancies(alloy_case):
     st = cm.make_state((8, 8, 8), ratio=(90, 6, 4), sigma=0.05, vacancies=40)
     w = cm.oracle_world(st)

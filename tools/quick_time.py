@@ -21,12 +21,12 @@ ctx.prepare()
 th0 = ctx.thermo()
 e0 = 0.5 * th0["mvv"] * synth.MVV2E + th0["pe"]
 ctx.step(3)
-for opt in ((1, 1), (0, 1), (1, 0)):
-    ctx.set_option("prune", opt[0]); ctx.set_option("fuse", opt[1])
+for opt in ((1, 1, 1), (0, 1, 1), (1, 1, 0)):
+    ctx.set_option("prune", opt[0]); ctx.set_option("fuse", opt[1]); ctx.set_option("smem", opt[2])
     ctx.step(2)
     ms = ctx.timed_steps(steps)
-    print("prune=%d fuse=%d: %.3f ms/step  %.3e atom-steps/s" % (opt[0], opt[1], ms / steps, ctx.n_owned * steps / (ms * 1e-3)), flush=True)
-ctx.set_option("prune", 1); ctx.set_option("fuse", 1)
+    print("prune=%d fuse=%d smem=%d: %.3f ms/step  %.3e atom-steps/s" % (opt[0], opt[1], opt[2], ms / steps, ctx.n_owned * steps / (ms * 1e-3)), flush=True)
+ctx.set_option("prune", 1); ctx.set_option("fuse", 1); ctx.set_option("smem", 1)
 ctx.profile_enable(True)
 ctx.step(steps)
 pr = ctx.profile_read()
