@@ -93,6 +93,14 @@ int misa_b200_set_neighbour_offsets(misa_b200_ctx *ctx, const int64_t *even, siz
 int misa_b200_make_neighbour_offsets(misa_b200_ctx *ctx, int cut_lattice, double cutoff_radius_factor);
 int misa_b200_get_neighbour_offsets(misa_b200_ctx *ctx, int which /*0 even,1 odd,2 half_even,3 half_odd*/,
                                     int64_t *out, size_t cap, size_t *n);
+/* Host-only planning (no CUDA device needed): the integer side of the path in the reference's index space.
+ * plan_offsets = NeighbourIndex::make for this sub-box's ghost-extended lattice; plan_halo = sendlist /
+ * recvlist of AtomList::exchangeAtomFirst (src/atom/atom_list.cpp:25-49, src/pack/lat_particle_packer.cpp:65-139)
+ * for message (dim, dir) plus the periodic image shift LatParticlePacker::setOffset adds on send. */
+int misa_b200_plan_offsets(const misa_b200_domain *dom, int cut_lattice, double cutoff_radius_factor, int which,
+                           int64_t *out, size_t cap, size_t *n);
+int misa_b200_plan_halo(const misa_b200_domain *dom, int dim, int dir, int64_t *send, int64_t *recv, size_t cap,
+                        size_t *n, double shift[3]);
 /* n_types species in atom_type enum order (Fe, Cu, Ni); phi is n_types*n_types, symmetric. */
 int misa_b200_set_potential(misa_b200_ctx *ctx, int n_types, const misa_b200_table *electron_density,
                             const misa_b200_table *embedded, const misa_b200_table *phi);

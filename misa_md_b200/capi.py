@@ -20,7 +20,7 @@ K_COUNT = len(K_NAMES)
 EXPORTS = [
     "misa_b200_env_init", "misa_b200_env_clean", "misa_b200_device_count", "misa_b200_last_error",
     "misa_b200_create", "misa_b200_destroy", "misa_b200_set_neighbour_offsets", "misa_b200_make_neighbour_offsets",
-    "misa_b200_get_neighbour_offsets", "misa_b200_set_potential",
+    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_set_potential",
     "misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc",
     "misa_b200_host_register", "misa_b200_host_unregister",
     "misa_b200_upload_atoms", "misa_b200_download_atoms", "misa_b200_upload_inter", "misa_b200_download_inter",
@@ -76,6 +76,8 @@ def load(build=True):
     L.misa_b200_set_neighbour_offsets.argtypes = [vp, i64p, C.c_size_t, i64p, C.c_size_t, i64p, C.c_size_t, i64p, C.c_size_t]
     L.misa_b200_make_neighbour_offsets.argtypes = [vp, i, d]
     L.misa_b200_get_neighbour_offsets.argtypes = [vp, i, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.misa_b200_plan_offsets.argtypes = [C.POINTER(Domain), i, d, i, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.misa_b200_plan_halo.argtypes = [C.POINTER(Domain), i, i, i64p, i64p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(d * 3)]
     L.misa_b200_set_potential.argtypes = [vp, i, C.POINTER(Table), C.POINTER(Table), C.POINTER(Table)]
     for fn in ("misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc"):
         getattr(L, fn).argtypes = [vp, vp, d]
@@ -143,6 +145,32 @@ def make_domain(phase_space, grid=(1, 1, 1), coord=(0, 0, 0), a=2.85532, crf=1.9
     dom.lattice_const = a
     dom.cutoff_radius_factor = crf
     return dom
+
+
+def plan_offsets(dom, which, cut_lattice=None, crf=None):
+    """Host-only: neighbour offsets (reference index space) of list `which` (0 even, 1 odd, 2 half_even, 3 half_odd)."""
+    import math
+    L = load()
+    crf = dom.cutoff_radius_factor if crf is None else crf
+    cut_lattice = int(math.ceil(crf)) if cut_lattice is None else cut_lattice
+    n = C.c_size_t()
+    _ck(L.misa_b200_plan_offsets(C.byref(dom), cut_lattice, crf, which, None, 0, C.byref(n)))
+    out = np.zeros(n.value, dtype=np.int64)
+    _ck(L.misa_b200_plan_offsets(C.byref(dom), cut_lattice, crf, which, out.ctypes.data_as(C.POINTER(C.c_int64)), n.value, C.byref(n)))
+    return out
+
+
+def plan_halo(dom, dim, direction):
+    """Host-only: (send indices, recv indices, shift[3]) of halo message (dim, direction), reference index space."""
+    L = load()
+    n = C.c_size_t()
+    _ck(L.misa_b200_plan_halo(C.byref(dom), dim, direction, None, None, 0, C.byref(n), None))
+    send = np.zeros(n.value, dtype=np.int64)
+    recv = np.zeros(n.value, dtype=np.int64)
+    shift = (C.c_double * 3)()
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    _ck(L.misa_b200_plan_halo(C.byref(dom), dim, direction, p(send), p(recv), n.value, C.byref(n), C.byref(shift)))
+    return send, recv, np.array(list(shift))
 
 
 class Context:

@@ -107,10 +107,28 @@ static int dmalloc(T **p, size_t n) {
     return 0;
 }
 
-static void build_halo_lists_host(const misa_b200_ctx *c, std::vector<int> send[3][2], std::vector<int> recv[3][2]) {
+static int geo_from_domain(const misa_b200_domain *dom, Geo &g) {
+    g.nx = dom->sub_box_lattice_size[0]; g.ny = dom->sub_box_lattice_size[1]; g.nz = dom->sub_box_lattice_size[2];
+    g.gx = dom->lattice_size_ghost[0]; g.gy = dom->lattice_size_ghost[1]; g.gz = dom->lattice_size_ghost[2];
+    g.sxc = g.nx + 2 * g.gx; g.sy = g.ny + 2 * g.gy; g.sz = g.nz + 2 * g.gz;
+    for (int k = 0; k < 3; k++) g.lo[k] = dom->sub_box_lattice_low[k];
+    g.n_ext = 2LL * g.sxc * g.sy * g.sz;
+    g.H = g.n_ext / 2;
+    g.n_cells_owned = (long long)g.nx * g.ny * g.nz;
+    g.a = dom->lattice_const;
+    const double cutoff_radius = dom->lattice_const * dom->cutoff_radius_factor; // reference src/atom.cpp:15
+    g.rc2 = cutoff_radius * cutoff_radius;
+    g.runaway2 = pow(0.2 * dom->lattice_const, 2.0);                             // reference src/atom.cpp:42
+    if (g.nx <= 0 || g.ny <= 0 || g.nz <= 0 || g.gx < 1 || g.gy < 1 || g.gz < 1 || g.n_ext >= (1LL << 31)) return -1;
+    // the staged exchange forwards a ghost-wide slab of OWNED sites: a sub-box thinner than its ghost shell
+    // would need second-neighbour messages, which neither the reference nor this library sends
+    if (g.nx < g.gx || g.ny < g.gy || g.nz < g.gz) return -1;
+    return 0;
+}
+
+static void build_halo_lists_host(const Geo &g, std::vector<int> send[3][2], std::vector<int> recv[3][2]) {
     // sendlist: comm::fwCommLocalRegion as used at reference src/atom/atom_list.cpp:33-40;
     // recvlist: slabs of LatPackerFirst::onReceive, reference src/pack/lat_particle_packer.cpp:65-76,97-108,128-139.
-    const Geo &g = c->geo;
     const int gh[3] = {2 * g.gx, g.gy, g.gz}, bx[3] = {2 * g.nx, g.ny, g.nz}, ex[3] = {2 * g.sxc, g.sy, g.sz};
     for (int d = 0; d < 3; d++)
         for (int dir = 0; dir < 2; dir++) {
@@ -143,18 +161,7 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     c->dom = *dom;
     c->device = g_device;
     Geo &g = c->geo;
-    g.nx = dom->sub_box_lattice_size[0]; g.ny = dom->sub_box_lattice_size[1]; g.nz = dom->sub_box_lattice_size[2];
-    g.gx = dom->lattice_size_ghost[0]; g.gy = dom->lattice_size_ghost[1]; g.gz = dom->lattice_size_ghost[2];
-    g.sxc = g.nx + 2 * g.gx; g.sy = g.ny + 2 * g.gy; g.sz = g.nz + 2 * g.gz;
-    for (int k = 0; k < 3; k++) g.lo[k] = dom->sub_box_lattice_low[k];
-    g.n_ext = 2LL * g.sxc * g.sy * g.sz;
-    g.H = g.n_ext / 2;
-    g.n_cells_owned = (long long)g.nx * g.ny * g.nz;
-    g.a = dom->lattice_const;
-    const double cutoff_radius = dom->lattice_const * dom->cutoff_radius_factor; // reference src/atom.cpp:15
-    g.rc2 = cutoff_radius * cutoff_radius;
-    g.runaway2 = pow(0.2 * dom->lattice_const, 2.0);                             // reference src/atom.cpp:42
-    if (g.nx <= 0 || g.ny <= 0 || g.nz <= 0 || g.gx < 1 || g.n_ext >= (1LL << 31)) {
+    if (geo_from_domain(dom, g) != 0) {
         delete c;
         return fail(MISA_B200_EINVAL, "misa_b200_create: bad sub-box sizes");
     }
@@ -172,7 +179,7 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
 
     // halo lists
     std::vector<int> send[3][2], recv[3][2];
-    build_halo_lists_host(c, send, recv);
+    build_halo_lists_host(c->geo, send, recv);
     c->all_self = true;
     size_t max_n = 0;
     for (int d = 0; d < 3; d++)
@@ -306,13 +313,11 @@ extern "C" int misa_b200_set_neighbour_offsets(misa_b200_ctx *c, const int64_t *
     return upload_offsets(c);
 }
 
-extern "C" int misa_b200_make_neighbour_offsets(misa_b200_ctx *c, int cut_lattice, double crf) {
-    // NeighbourIndex<T>::make, reference src/atom/neighbour_index.inl:13-76 (C++ % keeps the sign of xIndex)
-    REQ(c, MISA_B200_EINVAL, "null ctx");
-    const Geo &g = c->geo;
+// NeighbourIndex<T>::make, reference src/atom/neighbour_index.inl:13-76 (C++ % keeps the sign of xIndex)
+static void make_offsets_host(const Geo &g, int cut_lattice, double crf, std::vector<int64_t> out[4]) {
     const long long sx = 2LL * g.sxc, sy = g.sy;
     const double lim = crf + 2 * 0.5; // config::nei_lat_cutoff, reference src/md_building_config.h.in:24-29
-    for (int v = 0; v < 4; v++) c->ref_off[v].clear();
+    for (int v = 0; v < 4; v++) out[v].clear();
     for (int p = 0; p < 2; p++) {
         const double sgn = p == 0 ? 1.0 : -1.0;
         for (long long zi = -cut_lattice - 1; zi <= cut_lattice + 1; zi++)
@@ -326,13 +331,52 @@ extern "C" int misa_b200_make_neighbour_offsets(misa_b200_ctx *c, int cut_lattic
                         const bool neg_odd = xi < 0 && xi % 2 != 0;
                         const long long iy = neg_odd ? yi - (long long)sgn : yi, iz = neg_odd ? zi - (long long)sgn : zi;
                         const long long off = (iz * sy + iy) * sx + xi;
-                        c->ref_off[p].push_back(off);
+                        out[p].push_back(off);
                         const bool positive = z > 0 || (z == 0 && (y > 0 || (y == 0 && x > 0)));
-                        if (positive) c->ref_off[2 + p].push_back(off);
+                        if (positive) out[2 + p].push_back(off);
                     }
                 }
     }
+}
+
+extern "C" int misa_b200_make_neighbour_offsets(misa_b200_ctx *c, int cut_lattice, double crf) {
+    REQ(c, MISA_B200_EINVAL, "null ctx");
+    make_offsets_host(c->geo, cut_lattice, crf, c->ref_off);
     return upload_offsets(c);
+}
+
+// ---- host-only planning entry points (no CUDA device needed): the integer side of the path, exposed so that
+//      lattice indexing and halo ownership can be checked bit-exactly on any machine -------------------------
+extern "C" int misa_b200_plan_offsets(const misa_b200_domain *dom, int cut_lattice, double crf, int which, int64_t *out,
+                                      size_t cap, size_t *n) {
+    REQ(dom && n && which >= 0 && which < 4, MISA_B200_EINVAL, "misa_b200_plan_offsets: bad argument");
+    Geo g;
+    REQ(geo_from_domain(dom, g) == 0, MISA_B200_EINVAL, "misa_b200_plan_offsets: bad sub-box sizes");
+    std::vector<int64_t> v[4];
+    make_offsets_host(g, cut_lattice, crf, v);
+    *n = v[which].size();
+    if (out) for (size_t i = 0; i < std::min(cap, *n); i++) out[i] = v[which][i];
+    return MISA_B200_OK;
+}
+
+extern "C" int misa_b200_plan_halo(const misa_b200_domain *dom, int dim, int dir, int64_t *send, int64_t *recv, size_t cap,
+                                   size_t *n, double shift[3]) {
+    REQ(dom && n && dim >= 0 && dim < 3 && dir >= 0 && dir < 2, MISA_B200_EINVAL, "misa_b200_plan_halo: bad argument");
+    Geo g;
+    REQ(geo_from_domain(dom, g) == 0, MISA_B200_EINVAL, "misa_b200_plan_halo: bad sub-box sizes");
+    std::vector<int> s[3][2], r[3][2];
+    build_halo_lists_host(g, s, r);
+    *n = s[dim][dir].size();
+    for (size_t i = 0; i < std::min(cap, *n); i++) {
+        if (send) send[i] = dev_to_ref(s[dim][dir][i], g.H);
+        if (recv) recv[i] = dev_to_ref(r[dim][dir][i], g.H);
+    }
+    if (shift) { // periodic image shift, reference src/pack/lat_particle_packer.cpp:22-32
+        shift[0] = shift[1] = shift[2] = 0.0;
+        if (dom->grid_coord[dim] == 0 && dir == 0) shift[dim] = dom->meas_global_length[dim];
+        if (dom->grid_coord[dim] == dom->grid_size[dim] - 1 && dir == 1) shift[dim] = -dom->meas_global_length[dim];
+    }
+    return MISA_B200_OK;
 }
 
 extern "C" int misa_b200_get_neighbour_offsets(misa_b200_ctx *c, int which, int64_t *out, size_t cap, size_t *n) {

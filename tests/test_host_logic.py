@@ -1,0 +1,133 @@
+"""Host-side logic of the product checked on CPU against the oracle (which is pinned to the reference's own unit
+tests in test_oracle_kat.py): lattice indexing, halo ownership lists, setfl parsing + spline rows, initial state.
+Integer results must be bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import misa_md_b200 as mb
+from misa_md_b200 import capi, synth
+from oracle import oracle_py as O
+
+A, CRF = 2.85532, 1.96125
+CASES = [((8, 9, 10), (1, 1, 1), (0, 0, 0)), ((12, 8, 10), (2, 1, 1), (1, 0, 0)), ((12, 12, 12), (2, 2, 2), (1, 0, 1)),
+         ((16, 12, 20), (2, 2, 2), (0, 1, 1)), ((200, 200, 200), (2, 2, 2), (1, 1, 1))]
+
+
+@pytest.mark.parametrize("phase,grid,coord", CASES)
+def test_neighbour_offsets_bit_exact(phase, grid, coord):
+    dom = capi.make_domain(phase, grid, coord, A, CRF)
+    w = None
+    odom = O.make_domain(phase, grid, coord, A, CRF, ghost=3)
+    rk = O.Rank()
+    e = odom.dbx_ghost_extended_lattice_size
+    rk.size_x, rk.size_y, rk.size_z = e[0], e[1], e[2]
+    O.lib().ora_nei_make(C.byref(rk), odom.cut_lattice, CRF)
+    want = [v.to_numpy() for v in (rk.nei_even, rk.nei_odd, rk.nei_half_even, rk.nei_half_odd)]
+    for which in range(4):
+        got = capi.plan_offsets(dom, which)
+        assert np.array_equal(got, want[which])  # same values in the same order
+    assert len(want[0]) == 228 and len(want[2]) == 114
+
+
+@pytest.mark.parametrize("phase,grid,coord", CASES[:4])
+def test_halo_lists_bit_exact(phase, grid, coord, pot):
+    """sendlist / recvlist of AtomList::exchangeAtomFirst for this sub-box, and the periodic shifts."""
+    w = O.World(phase, grid=grid, a=A, crf=CRF, pot=pot)
+    w.fill_lattice()
+    w.L.ora_exchange_atom_first(w.h)
+    dom = capi.make_domain(phase, grid, coord, A, CRF)
+    rk = w.rank(dom.rank)
+    assert tuple(rk.dom.grid_coord) == tuple(coord)
+    for dim in range(3):
+        for direction in range(2):
+            send, recv, shift = capi.plan_halo(dom, dim, direction)
+            assert np.array_equal(send, rk.sendlist[2 * dim + direction].to_numpy())
+            assert np.array_equal(recv, rk.recvlist[2 * dim + direction].to_numpy())
+            want = np.zeros(3)
+            if coord[dim] == 0 and direction == 0:
+                want[dim] = phase[dim] * A
+            if coord[dim] == grid[dim] - 1 and direction == 1:
+                want[dim] = -(phase[dim] * A)
+            assert np.array_equal(shift, want)
+    w.close()
+
+
+def test_domain_matches_oracle_domain():
+    for phase, grid, coord in CASES:
+        d = capi.make_domain(phase, grid, coord, A, CRF)
+        o = O.make_domain(phase, grid, coord, A, CRF, ghost=3)
+        assert d.rank == o.rank
+        assert [list(r) for r in d.rank_id_neighbours] == [list(r) for r in o.rank_id_neighbours]
+        assert list(d.sub_box_lattice_size) == list(o.sub_box_lattice_size)
+        assert list(d.lattice_size_ghost) == list(o.lattice_size_ghost)
+        r = o.sub_box_lattice_region
+        assert list(d.sub_box_lattice_low) == [r.x_low, r.y_low, r.z_low]
+        assert list(d.meas_global_length) == list(o.meas_global_length)
+
+
+def test_setfl_reader_and_spline_rows_bit_exact(pot):
+    """The product's host-side setfl parser + array2spline give the oracle's coefficient rows to the last bit
+    (both restate libpot's interpolateFile; the GPU consumes exactly these rows)."""
+    p = capi.read_setfl(mb.SETFL_PATH)
+    assert p["keys"] == [26, 29, 28]
+    L = O.lib()
+
+    class PotTable(C.Structure):
+        _fields_ = [("n", C.c_int), ("dx", C.c_double), ("inv_dx", C.c_double), ("values", C.POINTER(C.c_double)),
+                    ("spline", C.POINTER(C.c_double))]
+
+    class PotEam(C.Structure):
+        _fields_ = [("n_ele", C.c_int), ("key", C.c_int * 3), ("mass", C.c_double * 3), ("lat_const", C.c_double * 3),
+                    ("n_rho", C.c_int), ("n_r", C.c_int), ("d_rho", C.c_double), ("d_r", C.c_double), ("cutoff", C.c_double),
+                    ("embed", PotTable * 3), ("elec", PotTable * 3), ("phi", (PotTable * 3) * 3)]
+
+    pe = C.cast(pot.h, C.POINTER(PotEam)).contents
+    assert pe.n_ele == 3
+
+    def rows(t):
+        return np.ctypeslib.as_array(t.spline, shape=((t.n + 1) * 7,))
+
+    for i in range(3):
+        for mine, theirs in ((p["elec"][i], pe.elec[i]), (p["embed"][i], pe.embed[i])):
+            assert mine[0] == theirs.n and mine[1] == theirs.inv_dx
+            assert np.array_equal(mine[2], rows(theirs))
+        for j in range(3):
+            assert np.array_equal(p["phi"][i][j][2], rows(pe.phi[i][j]))
+
+
+def test_mt19937_stream_is_std_mt19937():
+    # std::mt19937 default-seeded (5489) yields 3499211612 first and 4123659995 as its 10000th output
+    u = synth.mt19937_unit(5489, 10000)
+    assert int(round(u[0] * 4294967295.0)) == 3499211612
+    assert int(round(u[9999] * 4294967295.0)) == 4123659995
+
+
+def test_initial_state_rules():
+    st = synth.create_global_state((6, 7, 8), seed=466953, t_set=600.0, ratio=(97, 2, 1))
+    n = 2 * 6 * 7 * 8
+    m = synth.MASS[st["type"]]
+    p = (st["v"] * m[..., None]).reshape(-1, 3).sum(axis=0)
+    assert np.all(np.abs(p) < 1e-9)
+    t = float(((st["v"] ** 2).sum(axis=-1) * m).sum()) * synth.MVV2E / ((3 * n - 3) * synth.BOLTZ)
+    assert abs(t - 600.0) < 1e-9
+    # world_builder.cpp:120-124: body-centre sites sit at +a/2 in y and z
+    assert st["x"][0, 0, 1].tolist() == [0.5 * A, A / 2, A / 2]
+    assert set(np.unique(st["type"]).tolist()) <= {0, 1, 2}
+    arr, lay = synth.scatter_to_sub_box(st, (1, 1, 1), (0, 0, 0))
+    a3 = arr.reshape(lay["ext_shape"])
+    assert np.all(a3["type"][:3] == synth.INVALID) and np.all(a3[lay["owned"]]["type"] >= 0)
+    assert np.array_equal(a3[lay["owned"]]["id"].reshape(-1), np.arange(1, n + 1, dtype=np.uint64))
+
+
+def test_sub_box_state_matches_reference_builder_rule():
+    """create_sub_box_state draws per sub-box with one seed (the reference's per-rank rule) and places the
+    block at its global lattice position / ids."""
+    arr, lay = synth.create_sub_box_state((8, 8, 8), (2, 1, 1), (1, 0, 0))
+    own = arr.reshape(lay["ext_shape"])[lay["owned"]]
+    assert own.shape == (8, 8, 8)
+    assert own["x"][0, 0, 0].tolist() == [4 * A, 0.0, 0.0]
+    assert own["id"][0, 0, 0] == 1 + 8
+    loc = synth.create_global_state((4, 8, 8))
+    assert np.array_equal(own["v"], loc["v"])
