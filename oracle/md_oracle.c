@@ -310,6 +310,12 @@ long ora_rank_size(const ora_rank *rk) { return rk->size; }
 size_t ora_rank_n_inter(const ora_rank *rk) { return rk->n_inter; }
 ora_atom *ora_rank_inter(ora_rank *rk) { return rk->inter; }
 size_t ora_rank_n_ghost_inter(const ora_rank *rk) { return rk->n_ghost; }
+/* test helper: replace rank r's local inter-atom list (InterAtomList::addInterAtom per element) */
+void ora_test_set_inter(ora_world *w, int r, const ora_atom *atoms, size_t n) {
+    ora_rank *rk = &w->ranks[r];
+    rk->n_inter = 0;
+    for (size_t i = 0; i < n; i++) inter_push(&rk->inter, &rk->n_inter, &rk->cap_inter, &atoms[i]);
+}
 size_t ora_total_inter(const ora_world *w) {
     size_t n = 0;
     for (int r = 0; r < w->n_ranks; r++) n += w->ranks[r].n_inter;

@@ -160,6 +160,7 @@ double ora_temperature(const ora_world *w);         /* configuration::temperatur
 void ora_rescale(ora_world *w, double T);           /* configuration::rescale */
 double ora_potential_energy(ora_world *w);          /* ours: sum F(rho) + pair sum (needs rho current) */
 size_t ora_total_inter(const ora_world *w);
+void ora_test_set_inter(ora_world *w, int r, const ora_atom *atoms, size_t n); /* test helper */
 size_t ora_rank_n_inter(const ora_rank *rk);
 ora_atom *ora_rank_inter(ora_rank *rk);
 size_t ora_rank_n_ghost_inter(const ora_rank *rk);

@@ -1,0 +1,98 @@
+"""GPU parity on the off-lattice ("inter") atom path: PKA kick, run-away detection (atom::decide), inter-atom
+rho/force, vacancy re-occupation -- BASELINE.json configs[3] at test size. Occupancy, ids and the inter-atom set
+must be exact; positions/velocities/forces within the floating-point bars."""
+import numpy as np
+import pytest
+
+from tests import common as cm
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cascade(phase, energy, direction, lat, steps, dt, check_every=0):
+    st = cm.make_state(phase)
+    w = cm.oracle_world(st, dt=dt)
+    w.prepare()
+    ctx = cm.gpu_context(st, dt=dt)
+    ctx.prepare()
+    import ctypes as C
+    w.L.ora_collision_step(w.h, C.byref((C.c_int * 4)(*lat)), C.byref((C.c_double * 3)(*direction)), energy)
+    ctx.collision_step(lat, direction, energy)
+    seen_inter = 0
+    for s in range(steps):
+        w.step()
+        ctx.step(1)
+        if check_every and (s + 1) % check_every == 0:
+            th = ctx.thermo()
+            assert th["n_inter"] == w.total_inter(), s
+        seen_inter = max(seen_inter, w.total_inter())
+    return st, w, ctx, seen_inter
+
+
+def compare(w, ctx, xtol=1e-9, ftol=1e-7):
+    got = cm.owned(ctx, ctx.download())
+    ref = cm.owned(ctx, w.atoms(0))
+    assert np.array_equal(got["type"], ref["type"])           # vacancies exactly where the reference has them
+    valid = ref["type"] >= 0
+    assert np.array_equal(got["id"][valid], ref["id"][valid])   # and the same atoms on the same sites
+    assert cm.rel_err(got["x"][valid], ref["x"][valid]) < xtol
+    assert cm.rel_err(got["v"][valid], ref["v"][valid]) < 1e-6
+    assert cm.rel_err(got["f"][valid], ref["f"][valid]) < ftol
+    gi, ri = ctx.download_inter(), w.inter(0)
+    assert len(gi) == len(ri)
+    if len(ri):
+        assert np.array_equal(gi["id"], ri["id"])               # same inter atoms, same list order
+        assert np.array_equal(gi["type"], ri["type"])
+        assert cm.rel_err(gi["x"], ri["x"]) < xtol
+        assert cm.rel_err(gi["f"], ri["f"]) < ftol
+        assert cm.rel_err(gi["rho"], ri["rho"]) < 1e-9
+
+
+def test_pka_creates_inter_atoms_and_tracks_oracle():
+    st, w, ctx, seen = run_cascade((10, 10, 10), 300.0, (1.0, 3.0, 5.0), (5, 5, 5, 0), steps=120, dt=2e-4, check_every=10)
+    assert seen > 0, "the kick must drive at least one atom off its site"
+    compare(w, ctx)
+    th = ctx.thermo()
+    assert abs(th["mvv"] - w.L.ora_mvv(w.h)) / th["mvv"] < 1e-8
+    assert abs(th["pe"] - w.potential_energy()) / abs(th["pe"]) < 1e-9
+    ctx.close()
+    w.close()
+
+
+def test_pka_crossing_the_periodic_boundary():
+    """A PKA near the box face: inter atoms migrate through the periodic image (exchangeInter with the self
+    neighbour) and ghost inter atoms contribute across the boundary (borderInter)."""
+    st, w, ctx, seen = run_cascade((8, 8, 8), 400.0, (-3.0, -1.0, -0.5), (0, 1, 1, 0), steps=150, dt=2e-4, check_every=25)
+    assert seen > 0
+    compare(w, ctx)
+    ctx.close()
+    w.close()
+
+
+def test_uploaded_inter_atoms_static_parity():
+    """rho / df / force with interstitials and vacancies present from the start (no dynamics): one prepare()."""
+    st = cm.make_state((8, 8, 8), ratio=(90, 6, 4), sigma=0.04, vacancies=12)
+    rs = np.random.RandomState(5)
+    from misa_md_b200 import synth
+    inter = np.zeros(9, dtype=synth.ATOM_DTYPE)
+    inter["id"] = 100000 + np.arange(9)
+    inter["type"] = rs.randint(0, 3, size=9)
+    # octahedral-like interstitial positions well inside the box, >1.2 A from lattice atoms
+    cells = rs.randint(1, 7, size=(9, 3))
+    inter["x"] = (cells + np.array([0.5, 0.0, 0.03])) * cm.A
+    w = cm.oracle_world(st)
+    rk = w.rank(0)
+    import ctypes as C
+    buf = (C.c_char * (len(inter) * 104)).from_buffer_copy(inter.tobytes())
+    # hand the same list to the oracle: it owns realloc'd storage, so append through its own container
+    lib = w.L
+    lib.ora_test_set_inter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.ora_test_set_inter(w.h, 0, buf, len(inter))
+    w.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.upload_inter(inter)
+    ctx.prepare()
+    assert w.total_inter() == 9
+    compare(w, ctx, ftol=1e-9)
+    ctx.close()
+    w.close()

@@ -67,7 +67,7 @@ def test_smem_tables_match_generic_tables(ratio):
         ctx.set_option("smem", smem)
         ctx.prepare()
         out[smem] = cm.owned(ctx, ctx.download())
-        ref = cm.owned(ctx, w.atoms(0))
+        ref = cm.owned(ctx, w.atoms(0)).copy()  # w.atoms() is a view into the oracle's memory
         ctx.close()
     w.close()
     for smem in (1, 0):
