@@ -113,6 +113,8 @@ int misa_b200_set_potential(misa_b200_ctx *ctx, int n_types, const misa_b200_tab
 int misa_b200_eam_rho_calc(misa_b200_ctx *ctx, void *atoms, double cutoff_radius);
 int misa_b200_eam_df_calc(misa_b200_ctx *ctx, void *atoms, double cutoff_radius);
 int misa_b200_eam_force_calc(misa_b200_ctx *ctx, void *atoms, double cutoff_radius);
+/* number of AtomElement records in the ghost-extended array (AtomList::cap(), src/atom/atom_list.h:170-172) */
+int misa_b200_site_count(misa_b200_ctx *ctx, size_t *n_sites);
 /* page-lock the host AoS array once so the hook transfers run at PCIe speed (optional) */
 int misa_b200_host_register(void *ptr, size_t bytes);
 int misa_b200_host_unregister(void *ptr);

@@ -22,7 +22,7 @@ EXPORTS = [
     "misa_b200_create", "misa_b200_destroy", "misa_b200_set_neighbour_offsets", "misa_b200_make_neighbour_offsets",
     "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_set_potential",
     "misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc",
-    "misa_b200_host_register", "misa_b200_host_unregister",
+    "misa_b200_site_count", "misa_b200_host_register", "misa_b200_host_unregister",
     "misa_b200_upload_atoms", "misa_b200_download_atoms", "misa_b200_upload_inter", "misa_b200_download_inter",
     "misa_b200_set_timestep", "misa_b200_prepare", "misa_b200_step", "misa_b200_step_host", "misa_b200_setv", "misa_b200_collision_step",
     "misa_b200_rescale", "misa_b200_thermo", "misa_b200_sync",
@@ -81,6 +81,7 @@ def load(build=True):
     L.misa_b200_set_potential.argtypes = [vp, i, C.POINTER(Table), C.POINTER(Table), C.POINTER(Table)]
     for fn in ("misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc"):
         getattr(L, fn).argtypes = [vp, vp, d]
+    L.misa_b200_site_count.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.misa_b200_host_register.argtypes = [vp, C.c_size_t]
     L.misa_b200_host_unregister.argtypes = [vp]
     L.misa_b200_upload_atoms.argtypes = [vp, vp]

@@ -489,6 +489,11 @@ static int d2h_aos(misa_b200_ctx *c, void *atoms, int fields, int owned_only) {
     return 0;
 }
 
+extern "C" int misa_b200_site_count(misa_b200_ctx *c, size_t *n_sites) {
+    REQ(c && n_sites, MISA_B200_EINVAL, "null argument");
+    *n_sites = (size_t)c->geo.n_ext;
+    return 0;
+}
 extern "C" int misa_b200_host_register(void *ptr, size_t bytes) {
     CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
     return 0;
