@@ -152,6 +152,9 @@ int misa_b200_pass_verlet2(misa_b200_ctx *ctx); /* NewtonMotion::secondstep */
  * atom::decide (atom.cpp:42) is verified on the device (default on); "fuse": rho+df fused when no inter atoms. */
 int misa_b200_set_option(misa_b200_ctx *ctx, const char *name, int value);
 
+/* read-only introspection (tests, benches): "n_off", "n_full", "dmax", "single", "novac", "smem_bytes" */
+int misa_b200_query(misa_b200_ctx *ctx, const char *name, double *value);
+
 /* ---- multi-GPU: one sub-box per GPU, NCCL send/recv between face neighbours (replaces libcomm's
  *      comm::neiSendReceive over MPI; call sites atom.cpp:114,131,145, atom_list.cpp:45,53) ----- */
 int misa_b200_comm_unique_id(void *out128);

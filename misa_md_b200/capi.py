@@ -27,7 +27,7 @@ EXPORTS = [
     "misa_b200_set_timestep", "misa_b200_prepare", "misa_b200_step", "misa_b200_step_host", "misa_b200_setv", "misa_b200_collision_step",
     "misa_b200_rescale", "misa_b200_thermo", "misa_b200_sync",
     "misa_b200_pass_halo_x", "misa_b200_pass_clear", "misa_b200_pass_rho", "misa_b200_pass_df", "misa_b200_pass_halo_df",
-    "misa_b200_pass_force", "misa_b200_pass_verlet1", "misa_b200_pass_verlet2", "misa_b200_set_option",
+    "misa_b200_pass_force", "misa_b200_pass_verlet1", "misa_b200_pass_verlet2", "misa_b200_set_option", "misa_b200_query",
     "misa_b200_comm_unique_id", "misa_b200_comm_init", "misa_b200_comm_destroy",
     "misa_b200_profile_enable", "misa_b200_profile_read", "misa_b200_launch_count", "misa_b200_timed_steps",
 ]
@@ -58,6 +58,10 @@ def load(build=True):
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("MISA_B200_LIB")  # A/B timing of two builds of the SAME library; never a fallback
+    if override:
+        _build.LIB = override
+        build = False
     if build:
         try:
             _build.build()
@@ -101,6 +105,7 @@ def load(build=True):
                "misa_b200_comm_destroy"):
         getattr(L, fn).argtypes = [vp]
     L.misa_b200_set_option.argtypes = [vp, C.c_char_p, i]
+    L.misa_b200_query.argtypes = [vp, C.c_char_p, C.POINTER(d)]
     L.misa_b200_comm_unique_id.argtypes = [vp]
     L.misa_b200_comm_init.argtypes = [vp, vp, i, i]
     L.misa_b200_profile_enable.argtypes = [vp, i]
@@ -236,6 +241,11 @@ class Context:
 
     def set_option(self, name, value):
         _ck(self.L.misa_b200_set_option(self.h, name.encode(), int(value)))
+
+    def query(self, name):
+        v = C.c_double()
+        _ck(self.L.misa_b200_query(self.h, name.encode(), C.byref(v)))
+        return v.value
 
     # ---- compat hooks ------------------------------------------------------------------------
     def eam_rho_calc(self, atoms):

@@ -70,9 +70,17 @@ struct misa_b200_ctx {
     unsigned char *d_aos = nullptr;       // staging for AoS <-> SoA (n_ext * 104 B)
     // neighbour stencil, device-index space, per central parity
     std::vector<int64_t> ref_off[4];      // even, odd, half_even, half_odd in REFERENCE index space
-    int n_full = 0, n_pruned = 0;
+    int n_full = 0;
     int *d_off_full = nullptr;            // [2][n_full]
-    int *d_off_pruned = nullptr;          // [2][n_pruned]
+    // pruned stencils by displacement level L: every valid atom within L*0.01a of its site => two lattice atoms
+    // can only be within r_c if their SITES are closer than (crf + 0.02 L) a. L = 20 is atom::decide's own bound.
+    static const int kLevels = 21;
+    int level_n[kLevels] = {0};
+    size_t level_ofs[kLevels] = {0};
+    int *d_off_levels = nullptr;          // concatenated [L][2][level_n[L]]
+    double dmax2 = 0.0;                   // largest squared displacement from the ideal site (valid atoms, ghosts incl.)
+    bool dmax_valid = false;
+    unsigned long long *d_stepinfo = nullptr, *h_stepinfo = nullptr; // [0] off-lattice activity, [1] dmax2 bits
     // potential
     double *d_elec = nullptr, *d_embed = nullptr, *d_phi = nullptr;
     DevTables tab{};
@@ -83,7 +91,12 @@ struct misa_b200_ctx {
     unsigned long long *d_census = nullptr, *h_census = nullptr; // valid sites per species (ghost-extended array)
     unsigned long long census[MISA_MAX_TYPES] = {0, 0, 0};      // global (all sub-boxes) once prepare() ran
     bool census_valid = false;
+    int census_boxes = 1;                 // sub-boxes summed into d_census by the fetch in flight
     int sm_count = 0, smem_optin = 0;
+    cudaTextureObject_t tex_x[3] = {0, 0, 0}, tex_df = 0; // int2 views of x,y,z,df (TEX-pipe neighbour loads)
+    int opt_tex = 1, opt_novac = 1;
+    long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant
+    bool seen_offlattice = false;         // a run-away / inter atom was reported by any sub-box since the last census
     int opt_smem = 1;                     // use the shared-memory table kernels when possible
     double stage_r_lo = 2.0;              // tables are staged for r >= stage_r_lo (Angstrom)
     // halo
@@ -111,7 +124,6 @@ struct misa_b200_ctx {
     int last_runaways = 0;
     // options
     int opt_prune = 1, opt_fuse = 1;
-    bool invariant_ok = false;            // every valid lattice atom within 0.2a of its site (checked on device)
     // NCCL
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_size = 1;

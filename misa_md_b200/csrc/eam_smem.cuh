@@ -88,13 +88,9 @@ __device__ __forceinline__ double2 *stage_tables(const StagePlan &sp, unsigned c
 // int(p) is taken with a round-down add of 2^52 (p > 0): no F2I / I2F on the XU pipe.
 __device__ __forceinline__ int split_index(const double x, const double inv_dx, const int n, double &frac) {
     const double pp = fma(x, inv_dx, 1.0);
-    const double t = __dadd_rd(pp, 4503599627370496.0);
-    int m = __double2loint(t);
-    double mf = t - 4503599627370496.0;
-    if (m > n - 1 || m < 1) { // off the table: clamp like the reference
-        m = max(1, min(m, n - 1));
-        mf = (double)m;
-    }
+    const double t = __dadd_rd(pp, 4503599627370496.0);              // 2^52 + floor(pp): the integer sits in the low word
+    const int m = max(1, min(__double2loint(t), n - 1));            // clamp like the reference (off-table arguments)
+    const double mf = __hiloint2double(0x43300000, m) - 4503599627370496.0; // (double)m, exact, no conversion instruction
     frac = fmin(pp - mf, 1.0);
     return m;
 }
@@ -117,6 +113,25 @@ __device__ __forceinline__ Cubic fetch_cubic(const double2 *__restrict__ s_rows 
                                              const double2 *__restrict__ g_rows, const int row_lo, const int m) {
     if (s_rows != nullptr && m >= row_lo) return hermite(s_rows[m], s_rows[m + 1]);
     return hermite(__ldg(g_rows + m), __ldg(g_rows + m + 1));
+}
+
+// single-species path: rows (m, m+1) of a STAGED table through explicit shared-space loads (2 x LDS.128);
+// `base` = 32-bit shared address of the slot, biased by -row_lo rows. Rows below the staged range are rare
+// (r < r_lo only in close cascade encounters) and take a real branch to the global copy.
+__device__ __noinline__ void fetch_rows_global(const double2 *__restrict__ g_rows, const int m, double2 &a, double2 &b) {
+    a = __ldg(g_rows + m);
+    b = __ldg(g_rows + m + 1);
+}
+__device__ __forceinline__ Cubic fetch_cubic_s(const uint32_t base, const double2 *__restrict__ g_rows, const int row_lo, const int m) {
+    double2 a, b;
+    if (__builtin_expect(m >= row_lo, 1)) {
+        const uint32_t addr = base + ((uint32_t)m << 4);
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "r"(addr));
+        asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(b.x), "=d"(b.y) : "r"(addr));
+    } else {
+        fetch_rows_global(g_rows, m, a, b);
+    }
+    return hermite(a, b);
 }
 
 // per-CTA table directory in shared memory (multi-species path): pointers biased by -row_lo, nullptr if not staged
@@ -146,11 +161,37 @@ __device__ __forceinline__ int unit_to_dev(const Geo &g, const long long u, cons
     return owned_cell_to_dev(g, p, c, cx, y, z);
 }
 
+// ---- neighbour field access: plain global loads (LSU pipe) or texture fetches (TEX pipe of the same L1) -----
+struct SoaTex { cudaTextureObject_t x[3], df; };
+template <bool TEX> struct Nbr;
+template <> struct Nbr<false> {
+    const double *__restrict__ x, *__restrict__ y, *__restrict__ z, *__restrict__ df;
+    __device__ __forceinline__ Nbr(const Soa &s, const SoaTex &) : x(s.x[0]), y(s.x[1]), z(s.x[2]), df(s.df) {}
+    __device__ __forceinline__ double X(int j) const { return x[j]; }
+    __device__ __forceinline__ double Y(int j) const { return y[j]; }
+    __device__ __forceinline__ double Z(int j) const { return z[j]; }
+    __device__ __forceinline__ double DF(int j) const { return df[j]; }
+};
+template <> struct Nbr<true> {
+    cudaTextureObject_t x, y, z, df;
+    __device__ __forceinline__ Nbr(const Soa &, const SoaTex &t) : x(t.x[0]), y(t.x[1]), z(t.x[2]), df(t.df) {}
+    static __device__ __forceinline__ double f(cudaTextureObject_t t, int j) {
+        const int2 v = tex1Dfetch<int2>(t, j);
+        return __hiloint2double(v.y, v.x);
+    }
+    __device__ __forceinline__ double X(int j) const { return f(x, j); }
+    __device__ __forceinline__ double Y(int j) const { return f(y, j); }
+    __device__ __forceinline__ double Z(int j) const { return f(z, j); }
+    __device__ __forceinline__ double DF(int j) const { return f(df, j); }
+};
+
 // ---- K1 rho (+ K2 df fused): atom::latRho / latDf (reference src/atom.cpp:151-192,286-309), full-list gather ----
 // SINGLE: every valid site has type sp.single and tables 0 (elec) / 1 (phi) of the staging area are its own.
-template <bool SINGLE, bool FUSE_DF, bool ACCUM>
+// NOVAC: the census found no vacant site anywhere (ghosts included), so the per-neighbour type test is dropped.
+template <bool SINGLE, bool FUSE_DF, bool ACCUM, bool TEX = false, bool NOVAC = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off) {
+k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+    const Nbr<TEX> nb(s, tex);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ TabDir dir;
@@ -159,7 +200,7 @@ k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
     const long long upp = (g.n_cells_owned + 31) / 32;
-    const double2 *s_el0 = s_tab - sp.row_lo; // SINGLE: staged slot 0 = elec[single]
+    const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4); // SINGLE: staged slot 0 = elec[single]
     const double2 *g_el0 = sp.g_elec[SINGLE ? sp.single : 0];
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         const int d = unit_to_dev(g, u, upp, lane);
@@ -175,14 +216,14 @@ k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
 #pragma unroll 2
         for (int q = 0; q < n_off; q++) {
             const int j = d + off[q];
-            const int tj = s.type[j];
-            const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+            const int tj = (SINGLE && NOVAC) ? sp.single : s.type[j];
+            const double dx = xi - nb.X(j), dy = yi - nb.Y(j), dz = zi - nb.Z(j);
             const double d2 = dx * dx + dy * dy + dz * dz;
             if (tj >= 0 && d2 < g.rc2) {
                 const double r = d2 * rsqrt(d2);
                 double p;
                 const int m = split_index(r, tb.inv_dr, tb.n_r, p);
-                const Cubic c = SINGLE ? fetch_cubic(s_el0, g_el0, sp.row_lo, m) : fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
+                const Cubic c = SINGLE ? fetch_cubic_s(b_el0, g_el0, sp.row_lo, m) : fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
                 acc += cubic_value(c, p);
             }
         }
@@ -193,9 +234,10 @@ k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
 }
 
 // ---- K3 force: atom::latForce (reference src/atom.cpp:311-358), full-list gather ---------------------------
-template <bool SINGLE, bool ACCUM>
+template <bool SINGLE, bool ACCUM, bool TEX = false, bool NOVAC = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off) {
+k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+    const Nbr<TEX> nb(s, tex);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ TabDir dir;
@@ -205,8 +247,8 @@ k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
     const long long upp = (g.n_cells_owned + 31) / 32;
     const int nt = tb.n_types;
-    const double2 *s_el0 = s_tab - sp.row_lo;                       // SINGLE: slot 0 = elec[single]
-    const double2 *s_ph0 = s_tab + (size_t)sp.rows_s - sp.row_lo;   // SINGLE: slot 1 = phi[single][single]
+    const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);      // SINGLE: slot 0 = elec[single]
+    const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);                // SINGLE: slot 1 = phi[single][single]
     const double2 *g_el0 = sp.g_elec[SINGLE ? sp.single : 0];
     const double2 *g_ph0 = sp.g_phi[SINGLE ? sp.single * nt + sp.single : 0];
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
@@ -224,40 +266,40 @@ k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
 #pragma unroll 2
         for (int q = 0; q < n_off; q++) {
             const int j = d + off[q];
-            const int tj = s.type[j];
-            const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+            const int tj = (SINGLE && NOVAC) ? sp.single : s.type[j];
+            const double dx = xi - nb.X(j), dy = yi - nb.Y(j), dz = zi - nb.Z(j);
             const double d2 = dx * dx + dy * dy + dz * dz;
             if (tj >= 0 && d2 < g.rc2) {
                 const double recip = rsqrt(d2);
                 const double r = d2 * recip;
-                const double dfj = s.df[j];
+                const double dfj = nb.DF(j);
                 double p;
                 const int m = split_index(r, tb.inv_dr, tb.n_r, p);
+                // eam::toForce (oracle/pot.c:pot_to_force): phi = z2/r, phi' = z2'/r - phi/r, fpair = -(phi' + emb)/r with
+                // emb = rho'_i(r) df_j + rho'_j(r) df_i; z2' and rho' are slopes per knot times 1/dr, factored out:
+                //   fpair = -(1/r) * ( (1/dr) * (z2'_p / r + emb_p) - z2 / r^2 )
                 double z2, z2p, emb;
                 if (SINGLE) {
-                    const Cubic cp = fetch_cubic(s_ph0, g_ph0, sp.row_lo, m);
-                    const Cubic ce = fetch_cubic(s_el0, g_el0, sp.row_lo, m);
+                    const Cubic cp = fetch_cubic_s(b_ph0, g_ph0, sp.row_lo, m);
+                    const Cubic ce = fetch_cubic_s(b_el0, g_el0, sp.row_lo, m);
                     z2 = cubic_value(cp, p);
-                    z2p = cubic_slope(cp, p) * tb.inv_dr;
-                    const double rho_p = cubic_slope(ce, p) * tb.inv_dr;
-                    emb = rho_p * dfj + rho_p * dfi;
+                    z2p = cubic_slope(cp, p);
+                    emb = cubic_slope(ce, p) * (dfi + dfj);
                 } else {
                     const Cubic cp = fetch_cubic(dir.s_phi[ti * nt + tj], sp.g_phi[ti * nt + tj], sp.row_lo, m);
                     const Cubic ci = fetch_cubic(dir.s_elec[ti], sp.g_elec[ti], sp.row_lo, m);
                     z2 = cubic_value(cp, p);
-                    z2p = cubic_slope(cp, p) * tb.inv_dr;
-                    const double rho_p_from = cubic_slope(ci, p) * tb.inv_dr;
+                    z2p = cubic_slope(cp, p);
+                    const double rho_p_from = cubic_slope(ci, p);
                     double rho_p_to = rho_p_from;
                     if (tj != ti) {
                         const Cubic cj = fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
-                        rho_p_to = cubic_slope(cj, p) * tb.inv_dr;
+                        rho_p_to = cubic_slope(cj, p);
                     }
                     emb = rho_p_from * dfj + rho_p_to * dfi;
                 }
-                // eam::toForce (oracle/pot.c:pot_to_force): phi = z2/r, phi' = z2'/r - phi/r, fpair = -(phi' + emb)/r
-                const double phi = z2 * recip;
-                const double phip = z2p * recip - phi * recip;
-                const double fp = -(phip + emb) * recip;
+                const double t1 = fma(z2p, recip, emb);
+                const double fp = -recip * fma(tb.inv_dr, t1, -(z2 * (recip * recip)));
                 fx += dx * fp; fy += dy * fp; fz += dz * fp;
             }
         }

@@ -40,10 +40,11 @@ static std::map<misa_b200_ctx *, InterHost *> g_inter_host;
 static InterHost *IH(misa_b200_ctx *c) { return g_inter_host[c]; }
 
 // ---- device kernels ---------------------------------------------------------------------------------
-// counters[8] = this sub-box's off-lattice activity (run-aways of this step + listed inter atoms); [9] = global sum
-__global__ void k_activity(int *counters, const int n_listed) {
+// stepinfo[0] = this sub-box's off-lattice activity (run-aways of this step + listed inter atoms); the caller
+// reduces it (MAX) over the sub-boxes together with stepinfo[1], the dmax2 bit pattern written by k_verlet1
+__global__ void k_activity(int *counters, const int n_listed, unsigned long long *stepinfo) {
     counters[8] = counters[0] + n_listed;
-    counters[9] = counters[8];
+    stepinfo[0] = (unsigned long long)(counters[0] + n_listed);
 }
 __global__ void k_gather_sites(const int n, const int *__restrict__ sites, const Soa s, HostAtom *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -180,18 +180,19 @@ k_force(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ of
 //      bit-exact. Run-aways are appended to `runaway_sites` (device indices); the site is vacated by
 //      k_decide_vacate after the list has been sorted into the reference's k,j,i order. ------------------
 struct VerletPar { double dt; double c[MISA_MAX_TYPES]; };
-
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
-          int *__restrict__ runaway_sites, const int runaway_cap) {
-    const int p = blockIdx.x >= blocks_per_parity;
-    const int b = blockIdx.x - p * blocks_per_parity;
-    const long long c = (long long)b * blockDim.x + threadIdx.x;
-    if (c >= g.n_cells_owned) return;
+// max over the warp, then one atomicMax on the bit pattern (non-negative doubles order like unsigned integers)
+__device__ __forceinline__ void report_max(double v, unsigned long long *__restrict__ out) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+// squared displacement of the atom from its ideal site after the drift (0 for vacant sites)
+__device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const VerletPar &vp, const int p, const long long c,
+                                               int *__restrict__ counters, int *__restrict__ runaway_sites, const int runaway_cap) {
     int cx, y, z;
     const int d = owned_cell_to_dev(g, p, c, cx, y, z);
     const int t = s.type[d];
-    if (t < 0) return;
+    if (t < 0) return 0.0;
+
     const double cm = vp.c[t];
     double x[3];
 #pragma unroll
@@ -215,8 +216,20 @@ k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
         if (slot < runaway_cap) runaway_sites[slot] = d;
         else atomicExch(&counters[3], 1);
     }
+    return dist;
 }
 
+
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
+          int *__restrict__ runaway_sites, const int runaway_cap, unsigned long long *__restrict__ stepinfo) {
+    const int p = blockIdx.x >= blocks_per_parity;
+    const int b = blockIdx.x - p * blocks_per_parity;
+    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    double dist = 0.0;
+    if (c < g.n_cells_owned) dist = verlet1_site(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
+    report_max(dist, &stepinfo[1]);
+}
 // ---- K5 verlet-2: NewtonMotion::secondstep (reference src/newton_motion.cpp:57-74) -------------------
 __global__ void __launch_bounds__(MISA_BLOCK)
 k_verlet2(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity) {
@@ -348,23 +361,27 @@ k_soa_to_aos(const Geo g, unsigned long long *__restrict__ aos, const Soa s, con
     if (fields & F_DF) w[12] = __double_as_longlong(s.df[d]);
 }
 
-// ---- 0.2a invariant check (compat hooks): is every valid owned atom within 0.2a of its site? ---------
+// ---- largest squared displacement of any valid atom from its ideal site, over ALL ghost-extended sites (a
+//      ghost site's ideal position follows from its extended lattice index; images carry the periodic shift).
+//      Sizes the pruned stencil: two lattice atoms can only be within r_c if their SITES are closer than
+//      r_c + 2*dmax (atom::decide bounds dmax by 0.2a, reference src/atom.cpp:42). ---------------------------
 __global__ void __launch_bounds__(MISA_BLOCK)
-k_check_invariant(const Geo g, const Soa s, const int blocks_per_parity, int *__restrict__ counters) {
-    const int p = blockIdx.x >= blocks_per_parity;
-    const int b = blockIdx.x - p * blocks_per_parity;
-    const long long c = (long long)b * blockDim.x + threadIdx.x;
-    if (c >= g.n_cells_owned) return;
-    int cx, y, z;
-    const int d = owned_cell_to_dev(g, p, c, cx, y, z);
-    if (s.type[d] < 0) return;
-    const long long i = 2LL * cx + p;
-    const double xt = (double)(i + 2LL * g.lo[0]) * 0.5 * g.a;
-    const double yt = ((double)((long long)y + g.lo[1]) + (double)(i % 2) * 0.5) * g.a;
-    const double zt = ((double)((long long)z + g.lo[2]) + (double)(i % 2) * 0.5) * g.a;
-    const double ex = s.x[0][d] - xt, ey = s.x[1][d] - yt, ez = s.x[2][d] - zt;
-    // strict margin: anything not clearly inside 0.2a counts as a violation
-    if (ex * ex + ey * ey + ez * ez > g.runaway2 * (1.0 - 1e-9)) atomicAdd(&counters[4], 1);
+k_max_displacement(const Geo g, const Soa s, unsigned long long *__restrict__ out) {
+    const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double dist = 0.0;
+    if (d < g.n_ext && s.type[d] >= 0) {
+        const int p = d >= g.H;
+        const long long rem = d - (long long)p * g.H;
+        const int cx = (int)(rem % g.sxc);
+        const long long r = rem / g.sxc;
+        const int y = (int)(r % g.sy), z = (int)(r / g.sy);
+        const double xt = ((double)(cx - g.gx + g.lo[0]) + 0.5 * p) * g.a;
+        const double yt = ((double)(y - g.gy + g.lo[1]) + 0.5 * p) * g.a;
+        const double zt = ((double)(z - g.gz + g.lo[2]) + 0.5 * p) * g.a;
+        const double ex = s.x[0][d] - xt, ey = s.x[1][d] - yt, ez = s.x[2][d] - zt;
+        dist = ex * ex + ey * ey + ez * ez;
+    }
+    report_max(dist, out);
 }
 
 // ---- diagnostics: sum m v^2 (configuration::mvv, reference src/system_configuration.cpp:61-84), E_pot ---

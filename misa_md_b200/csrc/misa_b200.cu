@@ -85,11 +85,16 @@ static inline int nblk(long long n) { return (int)((n + MISA_BLOCK - 1) / MISA_B
 // -------------------------------------------------------------------------------------------------
 static int census_local(misa_b200_ctx *c);
 static int census_fetch(misa_b200_ctx *c);
+static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off);
+static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes);
+static inline bool no_vacancy(const misa_b200_ctx *c);
 static int smem_kernels_init(int optin) {
     static bool done = false;
     if (done) return 0;
 #define OPTIN(k) CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024)) /* static smem: mbarrier + table directory */
     OPTIN((k_rho_s<true, true, false>)); OPTIN((k_rho_s<true, false, false>)); OPTIN((k_rho_s<true, false, true>));
+    OPTIN((k_rho_s<true, true, false, true, false>)); OPTIN((k_rho_s<true, true, false, false, true>)); OPTIN((k_rho_s<true, true, false, true, true>));
+    OPTIN((k_force_s<true, false, true, false>)); OPTIN((k_force_s<true, false, false, true>)); OPTIN((k_force_s<true, false, true, true>));
     OPTIN((k_rho_s<false, true, false>)); OPTIN((k_rho_s<false, false, false>)); OPTIN((k_rho_s<false, false, true>));
     OPTIN((k_force_s<true, false>)); OPTIN((k_force_s<true, true>));
     OPTIN((k_force_s<false, false>)); OPTIN((k_force_s<false, true>));
@@ -171,9 +176,28 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.df, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n));
     for (int k = 0; k < 3; k++) { CU(cudaMemset(c->s.x[k], 0, n * 8)); CU(cudaMemset(c->s.v[k], 0, n * 8)); CU(cudaMemset(c->s.f[k], 0, n * 8)); }
     CU(cudaMemset(c->s.rho, 0, n * 8)); CU(cudaMemset(c->s.df, 0, n * 8)); CU(cudaMemset(c->s.type, 0xff, n)); CU(cudaMemset(c->s.id, 0, n * 8));
+    {
+        cudaResourceDesc rd;
+        cudaTextureDesc td;
+        double *fields[4] = {c->s.x[0], c->s.x[1], c->s.x[2], c->s.df};
+        cudaTextureObject_t *objs[4] = {&c->tex_x[0], &c->tex_x[1], &c->tex_x[2], &c->tex_df};
+        for (int k = 0; k < 4; k++) {
+            memset(&rd, 0, sizeof rd);
+            memset(&td, 0, sizeof td);
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = fields[k];
+            rd.res.linear.desc = cudaCreateChannelDesc<int2>();
+            rd.res.linear.sizeInBytes = n * sizeof(double);
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(objs[k], &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); *objs[k] = 0; }
+        }
+    }
     TRY(dmalloc(&c->d_counters, 16));
     CU(cudaMemset(c->d_counters, 0, 16 * sizeof(int)));
     CU(cudaMallocHost((void **)&c->h_counters, 16 * sizeof(int)));
+    TRY(dmalloc(&c->d_stepinfo, 4));
+    CU(cudaMemset(c->d_stepinfo, 0, 4 * sizeof(unsigned long long)));
+    CU(cudaMallocHost((void **)&c->h_stepinfo, 4 * sizeof(unsigned long long)));
     TRY(dmalloc(&c->d_reduce, 8));
     CU(cudaMallocHost((void **)&c->h_reduce, 8 * sizeof(double)));
 
@@ -237,8 +261,11 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaStreamSynchronize(c->stream);
     misa_b200_comm_destroy(c);
     for (int k = 0; k < 3; k++) { cudaFree(c->s.x[k]); cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
+    for (int k = 0; k < 3; k++) if (c->tex_x[k]) cudaDestroyTextureObject(c->tex_x[k]);
+    if (c->tex_df) cudaDestroyTextureObject(c->tex_df);
     cudaFree(c->s.rho); cudaFree(c->s.df); cudaFree(c->s.type); cudaFree(c->s.id);
-    cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_pruned);
+    cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
+    cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo);
     cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
     cudaFree(c->d_census); cudaFreeHost(c->h_census);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
@@ -278,26 +305,27 @@ static int upload_offsets(misa_b200_ctx *c) {
     REQ(c->ref_off[0].size() == c->ref_off[1].size() && !c->ref_off[0].empty(), MISA_B200_EINVAL,
         "neighbour offsets: even/odd lists must be non-empty and of equal length");
     c->n_full = (int)c->ref_off[0].size();
-    std::vector<int> full(2 * (size_t)c->n_full), pruned[2];
-    // pairs of LATTICE atoms can only be within the cutoff if their sites are closer than crf + 2*0.2
-    // (atom::decide keeps every lattice atom within 0.2a of its site, reference src/atom.cpp:42)
-    const double lim = c->dom.cutoff_radius_factor + 0.4;
+    std::vector<int> full(2 * (size_t)c->n_full), levels;
     for (int p = 0; p < 2; p++)
-        for (int q = 0; q < c->n_full; q++) {
-            const long long off = c->ref_off[p][q];
-            const int dv = ref_off_to_dev(off, p, g.H);
-            full[(size_t)p * c->n_full + q] = dv;
-            if (off_site_r2(off, p, g) < lim * lim) pruned[p].push_back(dv);
-        }
-    REQ(pruned[0].size() == pruned[1].size(), MISA_B200_EINVAL, "neighbour offsets: pruned lists differ in length");
-    c->n_pruned = (int)pruned[0].size();
-    cudaFree(c->d_off_full); cudaFree(c->d_off_pruned);
-    c->d_off_full = c->d_off_pruned = nullptr;
+        for (int q = 0; q < c->n_full; q++) full[(size_t)p * c->n_full + q] = ref_off_to_dev(c->ref_off[p][q], p, g.H);
+    // pairs of LATTICE atoms can only be within the cutoff if their sites are closer than crf + 2*dmax/a;
+    // atom::decide keeps dmax <= 0.2a (reference src/atom.cpp:42), the device measures the actual value.
+    for (int L = 0; L < misa_b200_ctx::kLevels; L++) {
+        const double lim = c->dom.cutoff_radius_factor + 0.02 * L + 1e-9;
+        int n[2] = {0, 0};
+        c->level_ofs[L] = levels.size();
+        for (int p = 0; p < 2; p++)
+            for (int q = 0; q < c->n_full; q++)
+                if (off_site_r2(c->ref_off[p][q], p, g) < lim * lim) { levels.push_back(full[(size_t)p * c->n_full + q]); n[p]++; }
+        REQ(n[0] == n[1], MISA_B200_EINVAL, "neighbour offsets: pruned lists differ in length");
+        c->level_n[L] = n[0];
+    }
+    cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
+    c->d_off_full = c->d_off_levels = nullptr;
     TRY(dmalloc(&c->d_off_full, full.size()));
-    TRY(dmalloc(&c->d_off_pruned, 2 * (size_t)c->n_pruned));
+    TRY(dmalloc(&c->d_off_levels, levels.size()));
     CU(cudaMemcpy(c->d_off_full, full.data(), full.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_off_pruned, pruned[0].data(), c->n_pruned * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_off_pruned + c->n_pruned, pruned[1].data(), c->n_pruned * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_off_levels, levels.data(), levels.size() * sizeof(int), cudaMemcpyHostToDevice));
     c->have_off = true;
     return MISA_B200_OK;
 }
@@ -509,7 +537,7 @@ extern "C" int misa_b200_upload_atoms(misa_b200_ctx *c, const void *atoms) {
     TRY(census_local(c));
     TRY(census_fetch(c));
     c->have_atoms = true;
-    c->invariant_ok = false;
+    c->dmax_valid = false;
     return 0;
 }
 extern "C" int misa_b200_download_atoms(misa_b200_ctx *c, void *atoms) {
@@ -542,7 +570,29 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     if (!strcmp(name, "prune")) c->opt_prune = value;
     else if (!strcmp(name, "fuse")) c->opt_fuse = value;
     else if (!strcmp(name, "smem")) c->opt_smem = value;
+    else if (!strcmp(name, "tex")) c->opt_tex = value;
+    else if (!strcmp(name, "novac")) c->opt_novac = value;
     else return fail(MISA_B200_EINVAL, std::string("unknown option ") + name);
+    return 0;
+}
+
+// read-only introspection for tests / benches: "n_off" (offsets the stencil kernels loop right now), "dmax"
+// (largest displacement from a site, Angstrom), "n_full", "single" (single-species fast path), "novac", "smem_bytes"
+extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value) {
+    REQ(c && name && value, MISA_B200_EINVAL, "null argument");
+    const int *offs;
+    int n_off;
+    pick_list(c, offs, n_off);
+    StagePlan sp;
+    size_t sb = 0;
+    const bool planned = c->have_pot && c->have_off && make_plan(c, sp, sb);
+    if (!strcmp(name, "n_off")) *value = n_off;
+    else if (!strcmp(name, "n_full")) *value = c->n_full;
+    else if (!strcmp(name, "dmax")) *value = c->dmax_valid ? sqrt(c->dmax2) : -1.0;
+    else if (!strcmp(name, "single")) *value = planned ? sp.single : -2;
+    else if (!strcmp(name, "novac")) *value = no_vacancy(c) ? 1 : 0;
+    else if (!strcmp(name, "smem_bytes")) *value = planned ? (double)sb : 0.0;
+    else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
     return 0;
 }
 
@@ -642,18 +692,31 @@ static int ready(misa_b200_ctx *c) {
     REQ(c->have_atoms, MISA_B200_ESTATE, "no atoms on the device");
     return 0;
 }
-static inline bool use_pruned(const misa_b200_ctx *c) { return c->opt_prune && c->invariant_ok && c->n_pruned > 0; }
 static inline bool has_inter(const misa_b200_ctx *c) { return c->n_inter_local + c->n_inter_ghost > 0; }
 
-static int check_invariant(misa_b200_ctx *c) {
-    const Geo &g = c->geo;
-    const int bpp = nblk(g.n_cells_owned);
-    CU(cudaMemsetAsync(c->d_counters + 4, 0, sizeof(int), c->stream));
-    k_check_invariant<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, bpp, c->d_counters);
+// The offset list the lattice stencil kernels loop: the smallest pruned level that the measured maximum
+// displacement allows, the reference's full list when nothing is known (or pruning is switched off).
+static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off) {
+    offs = c->d_off_full;
+    n_off = c->n_full;
+    if (!c->opt_prune || !c->dmax_valid) return;
+    const double d = sqrt(c->dmax2) + 1e-6;
+    const int L = (int)ceil(d / (0.01 * c->geo.a));
+    if (L >= misa_b200_ctx::kLevels || c->level_n[L] <= 0) return;
+    offs = c->d_off_levels + c->level_ofs[L];
+    n_off = c->level_n[L];
+}
+
+// measure dmax over the whole ghost-extended array (positions as they are now, ghosts included)
+static int measure_displacement(misa_b200_ctx *c) {
+    CU(cudaMemsetAsync(c->d_stepinfo + 1, 0, sizeof(unsigned long long), c->stream));
+    k_max_displacement<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo, c->s, c->d_stepinfo + 1);
     c->launches++;
-    CU(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_stepinfo + 1, c->d_stepinfo + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->invariant_ok = c->h_counters[4] == 0;
+    memcpy(&c->dmax2, c->h_stepinfo + 1, sizeof(double));
+    c->dmax_valid = true;
     return 0;
 }
 
@@ -690,10 +753,16 @@ static int census_local(misa_b200_ctx *c) {
     CU(cudaGetLastError());
     return 0;
 }
+static inline bool has_inter(const misa_b200_ctx *c);
 static int census_fetch(misa_b200_ctx *c) {
     CU(cudaMemcpyAsync(c->h_census, c->d_census, MISA_MAX_TYPES * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    for (int t = 0; t < MISA_MAX_TYPES; t++) c->census[t] = c->h_census[t];
+    unsigned long long valid = 0;
+    for (int t = 0; t < MISA_MAX_TYPES; t++) { c->census[t] = c->h_census[t]; valid += c->h_census[t]; }
+    // after prepare()'s all-reduce the counts cover every (equal-sized) sub-box
+    const unsigned long long boxes = (unsigned long long)std::max(c->census_boxes, 1);
+    c->n_valid_sites = valid % boxes == 0 ? (long long)(valid / boxes) : -1;
+    c->seen_offlattice = has_inter(c);
     c->census_valid = true;
     return 0;
 }
@@ -722,19 +791,35 @@ static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes)
     return smem_bytes + 1024 <= (size_t)c->smem_optin;
 }
 
+// No vacant site anywhere in the ghost-extended array: true once the census counted every site as valid and no
+// run-away has been seen since (decide() is the only thing that vacates a site; every rank learns of run-aways
+// anywhere through the per-step activity reduction, so a vacancy cannot enter the ghost shell unnoticed).
+static inline bool no_vacancy(const misa_b200_ctx *c) {
+    return c->opt_novac && c->n_valid_sites == c->geo.n_ext && !c->seen_offlattice;
+}
+
 static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
-    const bool pr = use_pruned(c);
-    const int *offs = pr ? c->d_off_pruned : c->d_off_full;
-    const int n_off = pr ? c->n_pruned : c->n_full;
+    const int *offs;
+    int n_off;
+    pick_list(c, offs, n_off);
     const size_t sm = (size_t)n_off * sizeof(int);
     Slot sl(c, MISA_B200_K_RHO);
     StagePlan sp;
     size_t sb;
     if (make_plan(c, sp, sb)) {
         const int grid = c->sm_count;
-#define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off)
+        SoaTex tex;
+        for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
+        tex.df = c->tex_df;
+        const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
+        const bool novac = no_vacancy(c);
+#define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+#define RHO_X(T, N) k_rho_s<true, true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+        if (sp.single >= 0 && fuse_df && !accum && (use_tex || novac)) {
+            if (use_tex && novac) RHO_X(true, true); else if (use_tex) RHO_X(true, false); else RHO_X(false, true);
+        } else
         if (sp.single >= 0) { if (accum) RHO_S(true, false, true); else if (fuse_df) RHO_S(true, true, false); else RHO_S(true, false, false); }
         else { if (accum) RHO_S(false, false, true); else if (fuse_df) RHO_S(false, true, false); else RHO_S(false, false, false); }
 #undef RHO_S
@@ -760,16 +845,25 @@ static int launch_df(misa_b200_ctx *c) {
 static int launch_force(misa_b200_ctx *c, bool accum) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
-    const bool pr = use_pruned(c);
-    const int *offs = pr ? c->d_off_pruned : c->d_off_full;
-    const int n_off = pr ? c->n_pruned : c->n_full;
+    const int *offs;
+    int n_off;
+    pick_list(c, offs, n_off);
     const size_t sm = (size_t)n_off * sizeof(int);
     Slot sl(c, MISA_B200_K_FORCE);
     StagePlan sp;
     size_t sb;
     if (make_plan(c, sp, sb)) {
         const int grid = c->sm_count;
-#define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off)
+        SoaTex tex;
+        for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
+        tex.df = c->tex_df;
+        const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
+        const bool novac = no_vacancy(c);
+#define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+#define FORCE_X(T, N) k_force_s<true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+        if (sp.single >= 0 && !accum && (use_tex || novac)) {
+            if (use_tex && novac) FORCE_X(true, true); else if (use_tex) FORCE_X(true, false); else FORCE_X(false, true);
+        } else
         if (sp.single >= 0) { if (accum) FORCE_S(true, true); else FORCE_S(true, false); }
         else { if (accum) FORCE_S(false, true); else FORCE_S(false, false); }
 #undef FORCE_S
@@ -811,13 +905,15 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
 // Agree across all sub-boxes whether any off-lattice atom exists this step (the list exchanges are collective
 // between neighbours, so every rank must take the same branch); also brings the step counters to the host.
 static int update_activity(misa_b200_ctx *c) {
-    k_activity<<<1, 1, 0, c->stream>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost);
+    k_activity<<<1, 1, 0, c->stream>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost, c->d_stepinfo);
     c->launches++;
-    if (c->comm_size > 1 && c->nccl_comm)
-        NC(g_nccl.AllReduce(c->d_counters + 8, c->d_counters + 9, 1, kNcclInt32, kNcclSum, c->nccl_comm, c->stream));
+    if (c->comm_size > 1 && c->nccl_comm) // [0] activity, [1] dmax2 bit pattern: MAX over the sub-boxes
+        NC(g_nccl.AllReduce(c->d_stepinfo, c->d_stepinfo, 2, kNcclUint64, kNcclMax, c->nccl_comm, c->stream));
     CU(cudaMemcpyAsync(c->h_counters, c->d_counters, 10 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_stepinfo, c->d_stepinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->inter_active = c->h_counters[9] > 0;
+    c->inter_active = c->h_stepinfo[0] > 0;
+    if (c->inter_active) c->seen_offlattice = true;
     return 0;
 }
 
@@ -831,16 +927,19 @@ extern "C" int misa_b200_pass_verlet1(misa_b200_ctx *c) {
     {
         Slot sl(c, MISA_B200_K_VERLET1);
         CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
-        k_verlet1<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap);
+        CU(cudaMemsetAsync(c->d_stepinfo, 0, 2 * sizeof(unsigned long long), c->stream));
+        k_verlet1<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
         c->launches++;
         CU(cudaGetLastError());
     }
     TRY(update_activity(c));
     REQ(c->h_counters[3] == 0, MISA_B200_EOVERFLOW, "run-away list overflow");
     c->last_runaways = c->h_counters[0];
-    // every lattice atom that is still (or again) on a site after decide() may sit further than 0.2a from it
-    // when run-aways re-occupied sites: fall back to the full stencil for this step.
-    c->invariant_ok = c->last_runaways == 0;
+    // k_verlet1 measured every owned atom after the drift and the reduction took the MAX over all sub-boxes, so
+    // the value also bounds every ghost. With off-lattice activity anywhere (run-aways leave, inter atoms may
+    // re-occupy vacancies far from the site) it is re-measured after the ghost exchange instead.
+    memcpy(&c->dmax2, c->h_stepinfo + 1, sizeof(double));
+    c->dmax_valid = !c->inter_active;
     if (c->inter_active) {
         Slot sl(c, MISA_B200_K_INTER);
         TRY(inter_decide(c, c->last_runaways));
@@ -885,10 +984,14 @@ extern "C" int misa_b200_prepare(misa_b200_ctx *c) {
     TRY(ready(c));
     TRY(misa_b200_pass_halo_x(c)); // exchangeAtomFirst: the lists are static, built in misa_b200_create
     TRY(census_local(c));          // ghosts are filled now; sum over sub-boxes so every rank plans alike
-    if (c->comm_size > 1 && c->nccl_comm)
+    c->census_boxes = 1;
+    if (c->comm_size > 1 && c->nccl_comm) {
         NC(g_nccl.AllReduce(c->d_census, c->d_census, MISA_MAX_TYPES, kNcclUint64, kNcclSum, c->nccl_comm, c->stream));
+        c->census_boxes = c->comm_size;
+    }
     TRY(census_fetch(c));
-    TRY(check_invariant(c));
+    c->census_boxes = 1;
+    TRY(measure_displacement(c));
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
     TRY(update_activity(c));
     if (c->inter_active) { TRY(inter_exchange(c)); TRY(inter_border(c)); }
@@ -902,6 +1005,7 @@ extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
     for (int s = 0; s < n_steps; s++) {
         TRY(misa_b200_pass_verlet1(c));
         TRY(misa_b200_pass_halo_x(c));
+        if (!c->dmax_valid) TRY(measure_displacement(c));
         // clearForce is folded into the stencil kernels' stores (owned sites are overwritten)
         if (has_inter(c)) TRY(inter_clear(c));
         TRY(compute_eam(c));
@@ -971,6 +1075,7 @@ extern "C" int misa_b200_collision_step(misa_b200_ctx *c, const int32_t lat[4], 
     TRY(misa_b200_setv(c, lat, direction, energy));
     if (c->inter_active) { TRY(inter_exchange(c)); TRY(inter_border(c)); }
     TRY(misa_b200_pass_halo_x(c));
+    TRY(measure_displacement(c));
     TRY(misa_b200_pass_clear(c));
     return compute_eam(c);
 }
@@ -1028,7 +1133,7 @@ extern "C" int misa_b200_eam_rho_calc(misa_b200_ctx *c, void *atoms, double cuto
     c->have_atoms = true;
     TRY(census_local(c));
     TRY(census_fetch(c));
-    TRY(check_invariant(c));
+    TRY(measure_displacement(c));
     TRY(launch_rho(c, false, true));
     return d2h_aos(c, atoms, F_RHO, 1);
 }
@@ -1045,7 +1150,7 @@ extern "C" int misa_b200_eam_force_calc(misa_b200_ctx *c, void *atoms, double cu
     c->have_atoms = true;
     TRY(census_local(c));
     TRY(census_fetch(c));
-    TRY(check_invariant(c));
+    TRY(measure_displacement(c));
     TRY(launch_force(c, true));
     return d2h_aos(c, atoms, F_F, 1);
 }

@@ -22,7 +22,7 @@ struct NcclApi {
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
-static const int kNcclDouble = 8, kNcclInt32 = 2, kNcclUint64 = 5, kNcclSum = 0;
+static const int kNcclDouble = 8, kNcclInt32 = 2, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2;
 
 static int nccl_load() {
     if (g_nccl.h) return 0;

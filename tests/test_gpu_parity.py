@@ -76,6 +76,31 @@ def test_smem_tables_match_generic_tables(ratio):
     assert cm.rel_err(out[1]["f"], out[0]["f"]) < 1e-11
 
 
+@pytest.mark.parametrize("tex,novac", [(1, 0), (0, 1), (1, 1)])
+def test_kernel_variants_match_oracle(tex, novac):
+    """TEX-pipe neighbour loads and the no-vacancy fast path (type test dropped) against the oracle, then with a
+    vacancy present (the census must switch the fast path off)."""
+    for vac in (0, 5):
+        st = cm.make_state((9, 9, 10), sigma=0.06, vacancies=vac)
+        w = cm.oracle_world(st)
+        w.prepare()
+        ctx = cm.gpu_context(st)
+        ctx.set_option("tex", tex)
+        ctx.set_option("novac", novac)
+        ctx.prepare()
+        for _ in range(3):
+            w.step()
+        ctx.step(3)
+        got = cm.owned(ctx, ctx.download())
+        ref = cm.owned(ctx, w.atoms(0))
+        valid = ref["type"] >= 0
+        assert np.array_equal(got["type"], ref["type"])
+        assert cm.rel_err(got["rho"][valid], ref["rho"][valid]) < TOL
+        assert cm.rel_err(got["f"][valid], ref["f"][valid]) < 1e-9
+        ctx.close()
+        w.close()
+
+
 def test_close_pairs_below_staged_range():
     """Pairs closer than the staged r range (r < 2 Angstrom) take the global Hermite rows: same results."""
     st = cm.make_state((8, 8, 8), sigma=0.0)

@@ -20,13 +20,19 @@ ctx.upload(arr)
 ctx.prepare()
 th0 = ctx.thermo()
 e0 = 0.5 * th0["mvv"] * synth.MVV2E + th0["pe"]
-ctx.step(3)
-for opt in ((1, 1, 1), (0, 1, 1), (1, 1, 0)):
-    ctx.set_option("prune", opt[0]); ctx.set_option("fuse", opt[1]); ctx.set_option("smem", opt[2])
+equil = int(sys.argv[3]) if len(sys.argv) > 3 else 300
+ctx.step(equil)  # let the lattice thermalise so that dmax (=> the pruned stencil level) is stationary
+print("after %d steps: dmax %.3f A, n_off %d of %d, novac %d" % (equil, ctx.query("dmax"), ctx.query("n_off"), ctx.query("n_full"), ctx.query("novac")), flush=True)
+for opt in ((1, 1, 1, 0, 0), (1, 1, 1, 0, 1), (1, 1, 1, 1, 0), (1, 1, 1, 1, 1), (0, 1, 1, 0, 1), (1, 1, 0, 0, 0)):
+    for k, name in enumerate(("prune", "fuse", "smem", "tex", "novac")):
+        ctx.set_option(name, opt[k])
     ctx.step(2)
     ms = ctx.timed_steps(steps)
-    print("prune=%d fuse=%d smem=%d: %.3f ms/step  %.3e atom-steps/s" % (opt[0], opt[1], opt[2], ms / steps, ctx.n_owned * steps / (ms * 1e-3)), flush=True)
-ctx.set_option("prune", 1); ctx.set_option("fuse", 1); ctx.set_option("smem", 1)
+    print("prune=%d fuse=%d smem=%d tex=%d novac=%d: %.3f ms/step  %.3e atom-steps/s" % (opt + (ms / steps, ctx.n_owned * steps / (ms * 1e-3))), flush=True)
+    ctx.profile_enable(True); ctx.step(5); pr = ctx.profile_read(); ctx.profile_enable(False)
+    print("     rho %.3f ms  force %.3f ms  verlet1 %.3f ms  (n_off %d, dmax %.3f A)" % (pr["rho"][0] / pr["rho"][1], pr["force"][0] / pr["force"][1], pr["verlet1"][0] / pr["verlet1"][1], ctx.query("n_off"), ctx.query("dmax")), flush=True)
+for k, name in enumerate(("prune", "fuse", "smem", "tex", "novac")):
+    ctx.set_option(name, (1, 1, 1, 0, 1)[k])
 ctx.profile_enable(True)
 ctx.step(steps)
 pr = ctx.profile_read()
