@@ -183,7 +183,11 @@ struct VerletPar { double dt; double c[MISA_MAX_TYPES]; };
 // max over the warp, then one atomicMax on the bit pattern (non-negative doubles order like unsigned integers)
 __device__ __forceinline__ void report_max(double v, unsigned long long *__restrict__ out) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+    if ((threadIdx.x & 31) == 0) {
+        // the running maximum only grows: a (possibly stale) plain read filters out almost every warp
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        if (bits > *reinterpret_cast<volatile unsigned long long *>(out)) atomicMax(out, bits);
+    }
 }
 // squared displacement of the atom from its ideal site after the drift (0 for vacant sites)
 __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const VerletPar &vp, const int p, const long long c,
