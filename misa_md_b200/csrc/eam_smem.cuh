@@ -108,13 +108,6 @@ __device__ __forceinline__ double cubic_value(const Cubic &c, const double p) { 
 // derivative w.r.t. p (multiply by 1/dx for d/dx)
 __device__ __forceinline__ double cubic_slope(const Cubic &c, const double p) { return (3.0 * c.s3 * p + 2.0 * c.s4) * p + c.d0; }
 
-// row pair (m, m+1) of a table: shared copy when staged and m >= row_lo, else the global Hermite copy
-__device__ __forceinline__ Cubic fetch_cubic(const double2 *__restrict__ s_rows /* biased by -row_lo, or nullptr */,
-                                             const double2 *__restrict__ g_rows, const int row_lo, const int m) {
-    if (s_rows != nullptr && m >= row_lo) return hermite(s_rows[m], s_rows[m + 1]);
-    return hermite(__ldg(g_rows + m), __ldg(g_rows + m + 1));
-}
-
 // single-species path: rows (m, m+1) of a STAGED table through explicit shared-space loads (2 x LDS.128);
 // `base` = 32-bit shared address of the slot, biased by -row_lo rows. Rows below the staged range are rare
 // (r < r_lo only in close cascade encounters) and take a real branch to the global copy.
@@ -134,22 +127,21 @@ __device__ __forceinline__ Cubic fetch_cubic_s(const uint32_t base, const double
     return hermite(a, b);
 }
 
-// per-CTA table directory in shared memory (multi-species path): pointers biased by -row_lo, nullptr if not staged
-struct TabDir {
-    const double2 *s_elec[MISA_MAX_TYPES];
-    const double2 *s_phi[MISA_MAX_TYPES * MISA_MAX_TYPES];
-};
-__device__ __forceinline__ void build_dir(TabDir *dir, const StagePlan &sp, const double2 *s_tab) {
-    if (threadIdx.x < MISA_MAX_TYPES) dir->s_elec[threadIdx.x] = nullptr;
-    if (threadIdx.x < MISA_MAX_TYPES * MISA_MAX_TYPES) dir->s_phi[threadIdx.x] = nullptr;
-    __syncthreads();
-    if (threadIdx.x < sp.n_staged) {
-        const int id = sp.staged_id[threadIdx.x];
-        const double2 *p = s_tab + (size_t)threadIdx.x * sp.rows_s - sp.row_lo;
-        if (id < MISA_MAX_TYPES) dir->s_elec[id] = p;
-        else dir->s_phi[id - MISA_MAX_TYPES] = p;
+// multi-species path: the majority species' tables are the staged ones (slot 0 = elec[maj], slot 1 = phi[maj][maj]);
+// every other table is read from the global Hermite block, table t at g_herm + t * (n_r + 1)
+// (t = type for elec, n_types + ti * n_types + tj for phi). Same arithmetic either way.
+__device__ __forceinline__ Cubic fetch_cubic_m(const bool staged, const uint32_t base, const double2 *__restrict__ g_rows, const int row_lo,
+                                               const int m) {
+    double2 a, b;
+    if (staged && m >= row_lo) {
+        const uint32_t addr = base + ((uint32_t)m << 4);
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "r"(addr));
+        asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(b.x), "=d"(b.y) : "r"(addr));
+    } else {
+        a = __ldg(g_rows + m);
+        b = __ldg(g_rows + m + 1);
     }
-    __syncthreads();
+    return hermite(a, b);
 }
 
 // warp work unit u -> owned cell of this lane (or -1)
@@ -194,14 +186,14 @@ k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const Nbr<TEX> nb(s, tex);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
-    __shared__ TabDir dir;
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
-    if (!SINGLE) build_dir(&dir, sp, s_tab);
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
     const long long upp = (g.n_cells_owned + 31) / 32;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4); // SINGLE: staged slot 0 = elec[single]
-    const double2 *g_el0 = sp.g_elec[SINGLE ? sp.single : 0];
+    const int maj = sp.staged_id[0];                 // species whose tables are staged (== sp.single when SINGLE)
+    const double2 *g_el0 = sp.g_elec[maj];
+    const size_t tstride = (size_t)tb.n_r + 1;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         const int d = unit_to_dev(g, u, upp, lane);
         if (d < 0) continue;
@@ -223,7 +215,8 @@ k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
                 const double r = d2 * rsqrt(d2);
                 double p;
                 const int m = split_index(r, tb.inv_dr, tb.n_r, p);
-                const Cubic c = SINGLE ? fetch_cubic_s(b_el0, g_el0, sp.row_lo, m) : fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
+                const Cubic c = SINGLE ? fetch_cubic_s(b_el0, g_el0, sp.row_lo, m)
+                                       : fetch_cubic_m(tj == maj, b_el0, sp.g_elec[0] + (size_t)tj * tstride, sp.row_lo, m);
                 acc += cubic_value(c, p);
             }
         }
@@ -240,17 +233,17 @@ k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const Nbr<TEX> nb(s, tex);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
-    __shared__ TabDir dir;
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
-    if (!SINGLE) build_dir(&dir, sp, s_tab);
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
     const long long upp = (g.n_cells_owned + 31) / 32;
     const int nt = tb.n_types;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);      // SINGLE: slot 0 = elec[single]
     const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);                // SINGLE: slot 1 = phi[single][single]
-    const double2 *g_el0 = sp.g_elec[SINGLE ? sp.single : 0];
-    const double2 *g_ph0 = sp.g_phi[SINGLE ? sp.single * nt + sp.single : 0];
+    const int maj = sp.staged_id[0];                 // species whose tables are staged (== sp.single when SINGLE)
+    const double2 *g_el0 = sp.g_elec[maj];
+    const double2 *g_ph0 = sp.g_phi[maj * nt + maj];
+    const size_t tstride = (size_t)tb.n_r + 1;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         const int d = unit_to_dev(g, u, upp, lane);
         if (d < 0) continue;
@@ -286,14 +279,15 @@ k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
                     z2p = cubic_slope(cp, p);
                     emb = cubic_slope(ce, p) * (dfi + dfj);
                 } else {
-                    const Cubic cp = fetch_cubic(dir.s_phi[ti * nt + tj], sp.g_phi[ti * nt + tj], sp.row_lo, m);
-                    const Cubic ci = fetch_cubic(dir.s_elec[ti], sp.g_elec[ti], sp.row_lo, m);
+                    const bool mi = ti == maj, mj = tj == maj;
+                    const Cubic cp = fetch_cubic_m(mi && mj, b_ph0, sp.g_phi[0] + (size_t)(ti * nt + tj) * tstride, sp.row_lo, m);
+                    const Cubic ci = fetch_cubic_m(mi, b_el0, sp.g_elec[0] + (size_t)ti * tstride, sp.row_lo, m);
                     z2 = cubic_value(cp, p);
                     z2p = cubic_slope(cp, p);
                     const double rho_p_from = cubic_slope(ci, p);
                     double rho_p_to = rho_p_from;
                     if (tj != ti) {
-                        const Cubic cj = fetch_cubic(dir.s_elec[tj], sp.g_elec[tj], sp.row_lo, m);
+                        const Cubic cj = fetch_cubic_m(mj, b_el0, sp.g_elec[0] + (size_t)tj * tstride, sp.row_lo, m);
                         rho_p_to = cubic_slope(cj, p);
                     }
                     emb = rho_p_from * dfj + rho_p_to * dfi;

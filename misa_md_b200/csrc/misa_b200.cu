@@ -96,6 +96,7 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_rho_s<true, true, false, true, false>)); OPTIN((k_rho_s<true, true, false, false, true>)); OPTIN((k_rho_s<true, true, false, true, true>));
     OPTIN((k_force_s<true, false, true, false>)); OPTIN((k_force_s<true, false, false, true>)); OPTIN((k_force_s<true, false, true, true>));
     OPTIN((k_rho_s<false, true, false>)); OPTIN((k_rho_s<false, false, false>)); OPTIN((k_rho_s<false, false, true>));
+    OPTIN((k_rho_s<false, true, false, true, false>)); OPTIN((k_force_s<false, false, true, false>));
     OPTIN((k_force_s<true, false>)); OPTIN((k_force_s<true, true>));
     OPTIN((k_force_s<false, false>)); OPTIN((k_force_s<false, true>));
 #undef OPTIN
@@ -820,6 +821,9 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
         if (sp.single >= 0 && fuse_df && !accum && (use_tex || novac)) {
             if (use_tex && novac) RHO_X(true, true); else if (use_tex) RHO_X(true, false); else RHO_X(false, true);
         } else
+        if (sp.single < 0 && fuse_df && !accum && use_tex)
+            k_rho_s<false, true, false, true, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex);
+        else
         if (sp.single >= 0) { if (accum) RHO_S(true, false, true); else if (fuse_df) RHO_S(true, true, false); else RHO_S(true, false, false); }
         else { if (accum) RHO_S(false, false, true); else if (fuse_df) RHO_S(false, true, false); else RHO_S(false, false, false); }
 #undef RHO_S
@@ -864,6 +868,9 @@ static int launch_force(misa_b200_ctx *c, bool accum) {
         if (sp.single >= 0 && !accum && (use_tex || novac)) {
             if (use_tex && novac) FORCE_X(true, true); else if (use_tex) FORCE_X(true, false); else FORCE_X(false, true);
         } else
+        if (sp.single < 0 && !accum && use_tex)
+            k_force_s<false, false, true, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex);
+        else
         if (sp.single >= 0) { if (accum) FORCE_S(true, true); else FORCE_S(true, false); }
         else { if (accum) FORCE_S(false, true); else FORCE_S(false, false); }
 #undef FORCE_S

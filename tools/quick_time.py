@@ -7,9 +7,10 @@ from misa_md_b200 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+ratio = tuple(int(v) for v in sys.argv[4:7]) if len(sys.argv) > 6 else (1, 0, 0)
 P = (n, n, n)
 t0 = time.time()
-st = synth.create_global_state(P)
+st = synth.create_global_state(P, ratio=ratio)
 print("state built %.1fs" % (time.time() - t0), flush=True)
 ctx = mb.Context(P)
 ctx.make_offsets()
