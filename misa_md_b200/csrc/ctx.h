@@ -95,6 +95,7 @@ struct misa_b200_ctx {
     int sm_count = 0, smem_optin = 0;
     cudaTextureObject_t tex_x[3] = {0, 0, 0}, tex_df = 0; // int2 views of x,y,z,df (TEX-pipe neighbour loads)
     int opt_tex = 1, opt_novac = 1;
+    int opt_fast = 1;                     // third-generation kernels (eam_fast.cuh)
     long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant
     bool seen_offlattice = false;         // a run-away / inter atom was reported by any sub-box since the last census
     int opt_smem = 1;                     // use the shared-memory table kernels when possible

@@ -1,0 +1,330 @@
+// misa_md_b200/csrc/eam_fast.cuh -- PRODUCTION rho / force kernels (round 1, third generation).
+//
+// What the ncu capture of the second generation (eam_smem.cuh, profiles/r01j_*) showed: neither the fp64 pipe
+// (53 %) nor the L1 data pipe was saturated; the kernels were ISSUE / LATENCY bound -- 100 warp instructions per
+// (atom, offset) iteration of which only 35 were fp64, the rest address arithmetic, constant reloads, texture
+// handle set-up, reconvergence barriers, the rsqrt slow-path test and a local-memory round trip around the
+// rare "row below the staged range" call. This generation removes that overhead:
+//   * neighbour fields stay on the TEXTURE pipe (its L1 data path is separate from the LSU path that carries the
+//     shared-memory table gathers); a packed {x,y,z,df} copy read with one 256-bit LSU load per neighbour was
+//     tried and rejected: it put 1216 more wavefronts per warp on the LSU pipe, which then saturated at 88 %
+//     (profiles/r01k_ncu_packed_summary.txt);
+//   * the in-range test is warp-uniform (__any_sync -> one vote + one branch, no BSSY/BSYNC): a warp is 32
+//     consecutive cells of one sub-lattice, so all lanes see the same lattice shell and agree almost always;
+//     lanes that are out of range compute along and their contribution is selected away;
+//   * rsqrt is MUFU.RSQ64H + the same third-order Newton step libdevice uses, without its special-case branch
+//     (0 < d2 < rc2 here);
+//   * rows below the staged range are not handled in the loop at all: the row index is clamped, the lane
+//     remembers that it happened, and after the loop such atoms (close cascade encounters only) are recomputed
+//     from the global tables by a separate out-of-line routine;
+//   * the Hermite cubic is evaluated in basis form (shared between the tables of one pair).
+// Multi-species boxes use the same loop: per-lane GENERIC table pointers (shared memory for the staged
+// majority tables, global memory for the rest) instead of divergent code paths.
+// Arithmetic differs from the reference's operation order only as documented in DESIGN.md 4.3 (<< 1e-10).
+#pragma once
+#include "eam_smem.cuh"
+
+// 1/sqrt(a) for 0 < a < inf, normal range: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
+//   e = 1 - a y0^2;  y = y0 + y0 e (1/2 + 3/8 e)            -> rel. error ~ 5/16 e^3, below 1 ulp
+__device__ __forceinline__ double rsqrt_fast(const double a) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    const double e = fma(-a, y0 * y0, 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
+
+struct Split { int m; double p; int m0; };
+// libpot findSpline (oracle/pot.c:table_find): pp = x*inv_dx + 1; m = clamp(int(pp), 1, n-1); p = min(pp - m, 1).
+// Additionally m is raised to row_lo (first staged row, >= 1); m0 is the index before that (the caller keeps
+// its minimum to learn whether any pair fell below the staged range).
+__device__ __forceinline__ Split split_fast(const double x, const double inv_dx, const int n_m1, const int row_lo) {
+    Split s;
+    const double pp = fma(x, inv_dx, 1.0);
+    const double t = __dadd_rd(pp, 4503599627370496.0);   // 2^52 + floor(pp): the integer sits in the low word
+    s.m0 = min(__double2loint(t), n_m1);
+    s.m = max(s.m0, row_lo);
+    const double mf = __hiloint2double(0x43300000, s.m) - 4503599627370496.0;
+    const double f = pp - mf;
+    s.p = f > 1.0 ? 1.0 : f;
+    return s;
+}
+
+// Hermite basis on [0,1] (value and d/dp), shared by every table looked up for one pair
+struct HBasis { double h01, h10, h11; };          // h00 = 1 - h01
+struct HSlope { double g01, g10, g11; };          // g00 = -g01
+__device__ __forceinline__ HBasis hbasis(const double p) {
+    HBasis b;
+    const double q = 1.0 - p, pq = p * q;
+    b.h01 = (p * p) * fma(-2.0, p, 3.0);
+    b.h10 = pq * q;
+    b.h11 = -pq * p;
+    return b;
+}
+__device__ __forceinline__ HSlope hslope(const double p) {
+    HSlope g;
+    const double q = 1.0 - p;
+    g.g01 = 6.0 * (p * q);
+    g.g11 = p * fma(3.0, p, -2.0);
+    g.g10 = g.g11 + (q - p);                       // 3p^2 - 4p + 1
+    return g;
+}
+__device__ __forceinline__ double hval(const HBasis &b, const double2 r0, const double2 r1) {
+    return fma(b.h11, r1.y, fma(b.h10, r0.y, fma(b.h01, r1.x - r0.x, r0.x)));
+}
+__device__ __forceinline__ double hder(const HSlope &g, const double2 r0, const double2 r1) {
+    return fma(g.g11, r1.y, fma(g.g10, r0.y, g.g01 * (r1.x - r0.x)));
+}
+
+// rows (m, m+1): shared-space loads for the single-species path, generic loads (shared or global window,
+// resolved per lane by the hardware) for the multi-species path
+__device__ __forceinline__ void rows_s(const uint32_t base, const int m, double2 &a, double2 &b) {
+    const uint32_t addr = base + ((uint32_t)m << 4);
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "r"(addr));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(b.x), "=d"(b.y) : "r"(addr));
+}
+__device__ __forceinline__ void rows_g(const unsigned long long base, const int m, double2 &a, double2 &b) {
+    const unsigned long long addr = base + ((unsigned long long)(unsigned)m << 4);
+    asm("ld.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "l"(addr));
+    asm("ld.v2.f64 {%0, %1}, [%2+16];" : "=d"(b.x), "=d"(b.y) : "l"(addr));
+}
+
+// per-CTA directory of generic table base addresses (biased so that base + 16 m is row m):
+//   [t] elec[t], [MISA_MAX_TYPES + ti * MISA_MAX_TYPES + tj] phi[ti][tj]
+#define EAM_DIR (MISA_MAX_TYPES + MISA_MAX_TYPES * MISA_MAX_TYPES)
+__device__ __forceinline__ void build_directory(unsigned long long *dir, const StagePlan &sp, const DevTables &tb, const double2 *s_tab) {
+    if (threadIdx.x < EAM_DIR) {
+        const int k = threadIdx.x, nt = tb.n_types;
+        unsigned long long a = 0;
+        int id = -1;
+        const double2 *g = nullptr;
+        if (k < MISA_MAX_TYPES) { if (k < nt) { g = sp.g_elec[k]; id = k; } }
+        else {
+            const int ti = (k - MISA_MAX_TYPES) / MISA_MAX_TYPES, tj = (k - MISA_MAX_TYPES) % MISA_MAX_TYPES;
+            if (ti < nt && tj < nt) { g = sp.g_phi[ti * nt + tj]; id = MISA_MAX_TYPES + ti * nt + tj; }
+        }
+        if (g) {
+            a = (unsigned long long)g;
+            for (int q = 0; q < sp.n_staged; q++)
+                if (sp.staged_id[q] == id)
+                    a = (unsigned long long)(s_tab + (size_t)q * sp.rows_s) - ((unsigned long long)sp.row_lo << 4); // generic address of the shared copy
+        }
+        dir[k] = a;
+    }
+}
+
+// ---- out-of-line recomputation of ONE atom from the global Hermite tables (close encounters: a pair below the
+//      staged range). Same arithmetic as the fast loop, no clamping to row_lo. ---------------------------------
+// Arguments are scalars / pointers by value on purpose: taking the address of a by-value kernel parameter struct
+// would move it (and every access in the hot loop) to local memory.
+__device__ __noinline__ double slow_rho_atom(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+                                             const int8_t *__restrict__ type, const int single,
+                                             const double2 *__restrict__ herm, const int n_r, const double inv_dr, const double rc2,
+                                             const int *__restrict__ off, const int n_off, const int d) {
+    const double xi = X[d], yi = Y[d], zi = Z[d];
+    const size_t tstride = (size_t)n_r + 1;
+    double acc = 0.0;
+    for (int q = 0; q < n_off; q++) {
+        const int j = d + off[q];
+        const int tj = type ? (int)type[j] : single;
+        const double dx = xi - X[j], dy = yi - Y[j], dz = zi - Z[j];
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (tj >= 0 && d2 < rc2) {
+            const double r = d2 * rsqrt_fast(d2);
+            const Split sx = split_fast(r, inv_dr, n_r - 1, 1);
+            const double2 *row = herm + (size_t)tj * tstride + sx.m;
+            acc += hval(hbasis(sx.p), __ldg(row), __ldg(row + 1));
+        }
+    }
+    return acc;
+}
+// herm: the global Hermite block, elec[t] at t * (n_r + 1), phi[ti][tj] at (nt + ti * nt + tj) * (n_r + 1)
+__device__ __noinline__ double3 slow_force_atom(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
+                                                const double *__restrict__ DF, const int8_t *__restrict__ type, const int single,
+                                                const double2 *__restrict__ herm, const int nt, const int n_r, const double inv_dr,
+                                                const double rc2, const int *__restrict__ off, const int n_off, const int d, const int ti) {
+    const double xi = X[d], yi = Y[d], zi = Z[d], dfi = DF[d];
+    const size_t tstride = (size_t)n_r + 1;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int q = 0; q < n_off; q++) {
+        const int j = d + off[q];
+        const int tj = type ? (int)type[j] : single;
+        const double dx = xi - X[j], dy = yi - Y[j], dz = zi - Z[j];
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        if (tj >= 0 && d2 < rc2) {
+            const double recip = rsqrt_fast(d2);
+            const Split sx = split_fast(d2 * recip, inv_dr, n_r - 1, 1);
+            const HBasis hb = hbasis(sx.p);
+            const HSlope hs = hslope(sx.p);
+            const double2 *rp = herm + (size_t)(nt + ti * nt + tj) * tstride + sx.m;
+            const double2 *ri = herm + (size_t)ti * tstride + sx.m;
+            const double2 *rj = herm + (size_t)tj * tstride + sx.m;
+            const double2 p0 = __ldg(rp), p1 = __ldg(rp + 1);
+            const double z2 = hval(hb, p0, p1), z2p = hder(hs, p0, p1);
+            const double emb = hder(hs, __ldg(ri), __ldg(ri + 1)) * DF[j] + hder(hs, __ldg(rj), __ldg(rj + 1)) * dfi;
+            const double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
+            fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
+        }
+    }
+    return make_double3(fx, fy, fz);
+}
+
+// ---- K1 rho (+ K2 df fused): atom::latRho / latDf (reference src/atom.cpp:151-192,286-309), full-list gather ----
+// SINGLE: every valid site has type sp.single; staged slot 0 = elec[single], slot 1 = phi[single][single].
+// NOVAC : the census found no vacant site (ghosts included) -> no per-neighbour type test.
+// ACCUM : add to the existing rho (compat hook semantics / inter-atom pass ran first) instead of overwriting.
+template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM>
+__global__ void __launch_bounds__(EAM_THREADS, 1)
+k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+    constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
+    const Nbr<true> nb(s, tex);
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    __shared__ unsigned long long dir[EAM_DIR];
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
+    if (!SINGLE) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
+    const int *s_off = reinterpret_cast<const int *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
+    const long long upp = (g.n_cells_owned + 31) / 32;
+    const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
+    const double rc2 = g.rc2, inv_dr = tb.inv_dr;
+    const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo;
+    for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
+        const int d0 = unit_to_dev(g, u, upp, lane);
+        const bool live = d0 >= 0;
+        const int d = live ? d0 : unit_to_dev(g, u, upp, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
+        const int ti = s.type[d];
+        const int par = u >= upp;
+        const int *off = s_off + (par ? n_off : 0);
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+        double acc = 0.0;
+        int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
+#pragma unroll 2
+        for (int q = 0; q < n_off; q++) {
+            const int j = d + off[q];
+            int tj = 0;
+            if (NEEDTYPE) tj = s.type[j];
+            const double dx = xi - nb.X(j), dy = yi - nb.Y(j), dz = zi - nb.Z(j);
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
+            if (__any_sync(0xffffffffu, in)) {
+                const double r = d2 * rsqrt_fast(d2);
+                const Split sx = split_fast(r, inv_dr, n_m1, row_lo);
+                mmin = min(mmin, sx.m0);
+                double2 r0, r1;
+                if (SINGLE) rows_s(b_el0, sx.m, r0, r1);
+                else rows_g(dir[max(tj, 0)], sx.m, r0, r1);
+                const double v = hval(hbasis(sx.p), r0, r1);
+                acc += in ? v : 0.0;
+            }
+        }
+        const bool low = mmin < row_lo;
+        if (__any_sync(0xffffffffu, low)) {
+            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], NEEDTYPE ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d);
+        }
+        if (!live) continue;
+        if (ti < 0) {
+            if (!ACCUM) s.rho[d] = 0.0;
+            continue;
+        }
+        if (ACCUM) acc += s.rho[d];
+        s.rho[d] = acc;
+        if (FUSE_DF) {
+            const double df = d_embed(tb, ti, acc);
+            s.df[d] = df;
+        }
+    }
+}
+
+// ---- K3 force: atom::latForce (reference src/atom.cpp:311-358), full-list gather ---------------------------
+// eam::toForce (oracle/pot.c:pot_to_force): phi = z2/r, phi' = z2'/r - phi/r, fpair = -(phi' + emb)/r with
+// emb = rho'_i(r) df_j + rho'_j(r) df_i; z2' and rho' are slopes per knot times 1/dr, factored out:
+//   fpair = -(1/r) * ( (1/dr) * (z2'_p / r + emb_p) - z2 / r^2 )
+template <bool SINGLE, bool NOVAC, bool ACCUM>
+__global__ void __launch_bounds__(EAM_THREADS, 1)
+k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+    constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
+    const Nbr<true> nb(s, tex);
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint64_t mbar;
+    __shared__ unsigned long long dir[EAM_DIR];
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
+    if (!SINGLE) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
+    const int *s_off = reinterpret_cast<const int *>(smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
+    const long long upp = (g.n_cells_owned + 31) / 32;
+    const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
+    const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);
+    const double rc2 = g.rc2, inv_dr = tb.inv_dr;
+    const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo;
+    for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
+        const int d0 = unit_to_dev(g, u, upp, lane);
+        const bool live = d0 >= 0;
+        const int d = live ? d0 : unit_to_dev(g, u, upp, 0);
+        const int ti = s.type[d];
+        const int tic = max(ti, 0);
+        const int par = u >= upp;
+        const int *off = s_off + (par ? n_off : 0);
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
+        unsigned long long d_eli = 0;
+        if (!SINGLE) d_eli = dir[tic];
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
+#pragma unroll 2
+        for (int q = 0; q < n_off; q++) {
+            const int j = d + off[q];
+            int tj = 0;
+            if (NEEDTYPE) tj = s.type[j];
+            const double dx = xi - nb.X(j), dy = yi - nb.Y(j), dz = zi - nb.Z(j);
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
+            if (__any_sync(0xffffffffu, in)) {
+                const double recip = rsqrt_fast(d2);
+                const double dfj = nb.DF(j);
+                const Split sx = split_fast(d2 * recip, inv_dr, n_m1, row_lo);
+                mmin = min(mmin, sx.m0);
+                const HBasis hb = hbasis(sx.p);
+                const HSlope hs = hslope(sx.p);
+                double z2, z2p, emb;
+                double2 r0, r1;
+                if (SINGLE) {
+                    rows_s(b_ph0, sx.m, r0, r1);
+                    z2 = hval(hb, r0, r1);
+                    z2p = hder(hs, r0, r1);
+                    rows_s(b_el0, sx.m, r0, r1);
+                    emb = hder(hs, r0, r1) * (dfi + dfj);
+                } else {
+                    const int tjc = max(tj, 0);
+                    rows_g(dir[MISA_MAX_TYPES + tic * MISA_MAX_TYPES + tjc], sx.m, r0, r1);
+                    z2 = hval(hb, r0, r1);
+                    z2p = hder(hs, r0, r1);
+                    rows_g(d_eli, sx.m, r0, r1);
+                    const double rho_p_from = hder(hs, r0, r1);
+                    double rho_p_to = rho_p_from;
+                    if (__any_sync(0xffffffffu, tjc != tic)) {
+                        rows_g(dir[tjc], sx.m, r0, r1);
+                        rho_p_to = hder(hs, r0, r1);
+                    }
+                    emb = fma(rho_p_from, dfj, rho_p_to * dfi);
+                }
+                double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
+                fp = in ? fp : 0.0;
+                fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
+            }
+        }
+        const bool low = mmin < row_lo;
+        if (__any_sync(0xffffffffu, low)) {
+            if (low) {
+                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, NEEDTYPE ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types, tb.n_r, inv_dr, rc2,
+                                                  offs + (par ? n_off : 0), n_off, d, tic);
+                fx = f.x; fy = f.y; fz = f.z;
+            }
+        }
+        if (!live) continue;
+        if (ti < 0) {
+            if (!ACCUM) { s.f[0][d] = 0.0; s.f[1][d] = 0.0; s.f[2][d] = 0.0; }
+            continue;
+        }
+        if (ACCUM) { fx += s.f[0][d]; fy += s.f[1][d]; fz += s.f[2][d]; }
+        s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz;
+    }
+}

@@ -17,6 +17,7 @@
 #include "nccl_dl.cuh"
 #include "inter.cuh"
 #include "eam_smem.cuh"
+#include "eam_fast.cuh"
 
 extern "C" const char *misa_b200_last_error(void) { return g_err.c_str(); }
 
@@ -99,6 +100,12 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_rho_s<false, true, false, true, false>)); OPTIN((k_force_s<false, false, true, false>));
     OPTIN((k_force_s<true, false>)); OPTIN((k_force_s<true, true>));
     OPTIN((k_force_s<false, false>)); OPTIN((k_force_s<false, true>));
+    OPTIN((k_rho_f<true, true, true, false>)); OPTIN((k_rho_f<true, true, false, false>)); OPTIN((k_rho_f<true, true, false, true>));
+    OPTIN((k_rho_f<true, false, true, false>)); OPTIN((k_rho_f<true, false, false, false>)); OPTIN((k_rho_f<true, false, false, true>));
+    OPTIN((k_rho_f<false, false, true, false>)); OPTIN((k_rho_f<false, false, false, false>)); OPTIN((k_rho_f<false, false, false, true>));
+    OPTIN((k_force_f<true, true, false>)); OPTIN((k_force_f<true, true, true>));
+    OPTIN((k_force_f<true, false, false>)); OPTIN((k_force_f<true, false, true>));
+    OPTIN((k_force_f<false, false, false>)); OPTIN((k_force_f<false, false, true>));
 #undef OPTIN
     done = true;
     return 0;
@@ -573,6 +580,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "smem")) c->opt_smem = value;
     else if (!strcmp(name, "tex")) c->opt_tex = value;
     else if (!strcmp(name, "novac")) c->opt_novac = value;
+    else if (!strcmp(name, "fast")) c->opt_fast = value;
     else return fail(MISA_B200_EINVAL, std::string("unknown option ") + name);
     return 0;
 }
@@ -809,6 +817,21 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
     Slot sl(c, MISA_B200_K_RHO);
     StagePlan sp;
     size_t sb;
+    if (c->opt_fast && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df && make_plan(c, sp, sb)) {
+        const int grid = c->sm_count;
+        const bool novac = no_vacancy(c), single = sp.single >= 0;
+        SoaTex tex;
+        for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
+        tex.df = c->tex_df;
+#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+#define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
+        if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
+#undef RHO_FA
+#undef RHO_F
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (make_plan(c, sp, sb)) {
         const int grid = c->sm_count;
         SoaTex tex;
@@ -856,6 +879,20 @@ static int launch_force(misa_b200_ctx *c, bool accum) {
     Slot sl(c, MISA_B200_K_FORCE);
     StagePlan sp;
     size_t sb;
+    if (c->opt_fast && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df && make_plan(c, sp, sb)) {
+        const int grid = c->sm_count;
+        const bool novac = no_vacancy(c), single = sp.single >= 0;
+        SoaTex tex;
+        for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
+        tex.df = c->tex_df;
+#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex); \
+                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex); } while (0)
+        if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
+#undef FORCE_F
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (make_plan(c, sp, sb)) {
         const int grid = c->sm_count;
         SoaTex tex;
