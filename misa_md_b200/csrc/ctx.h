@@ -76,6 +76,8 @@ struct misa_b200_ctx {
     // can only be within r_c if their SITES are closer than (crf + 0.02 L) a. L = 20 is atom::decide's own bound.
     static const int kLevels = 21;
     int level_n[kLevels] = {0};
+    int level_near[kLevels] = {0};        // leading entries (lists are sorted by site distance) that are almost surely in range
+    int near_full = 0;
     size_t level_ofs[kLevels] = {0};
     int *d_off_levels = nullptr;          // concatenated [L][2][level_n[L]]
     double dmax2 = 0.0;                   // largest squared displacement from the ideal site (valid atoms, ghosts incl.)
@@ -94,6 +96,9 @@ struct misa_b200_ctx {
     int census_boxes = 1;                 // sub-boxes summed into d_census by the fetch in flight
     int sm_count = 0, smem_optin = 0;
     cudaTextureObject_t tex_x[3] = {0, 0, 0}, tex_df = 0; // int2 views of x,y,z,df (TEX-pipe neighbour loads)
+    double *d_xyzd = nullptr;             // ONE allocation behind s.x[0..2] and s.df, field stride xyzd_stride doubles
+    long long xyzd_stride = 0;
+    cudaTextureObject_t tex_all = 0;      // int2 view of the whole block: one handle for all four fields (eam_fast.cuh)
     int opt_tex = 1, opt_novac = 1;
     int opt_fast = 1;                     // third-generation kernels (eam_fast.cuh)
     long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant

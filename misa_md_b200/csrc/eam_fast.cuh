@@ -23,6 +23,14 @@
 // Arithmetic differs from the reference's operation order only as documented in DESIGN.md 4.3 (<< 1e-10).
 #pragma once
 #include "eam_smem.cuh"
+#ifndef EAM_UNROLL_NEAR
+#define EAM_UNROLL_NEAR 2
+#endif
+#ifndef EAM_UNROLL_FAR
+#define EAM_UNROLL_FAR 2
+#endif
+#define EAM_PRAGMA(x) _Pragma(#x)
+#define EAM_UNROLL(n) EAM_PRAGMA(unroll n)
 
 // 1/sqrt(a) for 0 < a < inf, normal range: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
 //   e = 1 - a y0^2;  y = y0 + y0 e (1/2 + 3/8 e)            -> rel. error ~ 5/16 e^3, below 1 ulp
@@ -168,15 +176,24 @@ __device__ __noinline__ double3 slow_force_atom(const double *__restrict__ X, co
     return make_double3(fx, fy, fz);
 }
 
+// one texture handle for x, y, z and df (one allocation, field stride `ns` doubles; ctx.h d_xyzd)
+struct TexAll { cudaTextureObject_t t; int ns; };
+__device__ __forceinline__ double tex_f64(const cudaTextureObject_t t, const int i) {
+    const int2 v = tex1Dfetch<int2>(t, i);
+    return __hiloint2double(v.y, v.x);
+}
+
 // ---- K1 rho (+ K2 df fused): atom::latRho / latDf (reference src/atom.cpp:151-192,286-309), full-list gather ----
 // SINGLE: every valid site has type sp.single; staged slot 0 = elec[single], slot 1 = phi[single][single].
 // NOVAC : the census found no vacant site (ghosts included) -> no per-neighbour type test.
 // ACCUM : add to the existing rho (compat hook semantics / inter-atom pass ran first) instead of overwriting.
+// The offset list is sorted by site separation; its first n_near entries (sites >= 0.1a inside the cutoff) are
+// evaluated without any branch (two independent pairs in flight per thread), the rest behind a warp vote.
 template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const int n_near,
+        const TexAll tex) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
-    const Nbr<true> nb(s, tex);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
@@ -187,7 +204,8 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const long long upp = (g.n_cells_owned + 31) / 32;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
     const double rc2 = g.rc2, inv_dr = tb.inv_dr;
-    const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo;
+    const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo, ns = tex.ns;
+    const cudaTextureObject_t tx = tex.t;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         const int d0 = unit_to_dev(g, u, upp, lane);
         const bool live = d0 >= 0;
@@ -198,24 +216,34 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double acc = 0.0;
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
-#pragma unroll 2
-        for (int q = 0; q < n_off; q++) {
+        auto pair = [&](const double d2, const bool in, const int tj) {
+            const double r = d2 * rsqrt_fast(d2);
+            const Split sx = split_fast(r, inv_dr, n_m1, row_lo);
+            mmin = min(mmin, (NEEDTYPE && !in) ? 0x7fffffff : sx.m0);
+            double2 r0, r1;
+            if (SINGLE) rows_s(b_el0, sx.m, r0, r1);
+            else rows_g(dir[max(tj, 0)], sx.m, r0, r1);
+            const double v = hval(hbasis(sx.p), r0, r1);
+            acc += in ? v : 0.0;
+        };
+EAM_UNROLL(EAM_UNROLL_NEAR)
+        for (int q = 0; q < n_near; q++) {
             const int j = d + off[q];
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
-            const double dx = xi - nb.X(j), dy = yi - nb.Y(j), dz = zi - nb.Z(j);
+            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            pair(d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj);
+        }
+EAM_UNROLL(EAM_UNROLL_FAR)
+        for (int q = n_near; q < n_off; q++) {
+            const int j = d + off[q];
+            int tj = 0;
+            if (NEEDTYPE) tj = s.type[j];
+            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
-            if (__any_sync(0xffffffffu, in)) {
-                const double r = d2 * rsqrt_fast(d2);
-                const Split sx = split_fast(r, inv_dr, n_m1, row_lo);
-                mmin = min(mmin, sx.m0);
-                double2 r0, r1;
-                if (SINGLE) rows_s(b_el0, sx.m, r0, r1);
-                else rows_g(dir[max(tj, 0)], sx.m, r0, r1);
-                const double v = hval(hbasis(sx.p), r0, r1);
-                acc += in ? v : 0.0;
-            }
+            if (__any_sync(0xffffffffu, in)) pair(d2, in, tj);
         }
         const bool low = mmin < row_lo;
         if (__any_sync(0xffffffffu, low)) {
@@ -228,10 +256,7 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         }
         if (ACCUM) acc += s.rho[d];
         s.rho[d] = acc;
-        if (FUSE_DF) {
-            const double df = d_embed(tb, ti, acc);
-            s.df[d] = df;
-        }
+        if (FUSE_DF) s.df[d] = d_embed(tb, ti, acc);
     }
 }
 
@@ -241,9 +266,9 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
 //   fpair = -(1/r) * ( (1/dr) * (z2'_p / r + emb_p) - z2 / r^2 )
 template <bool SINGLE, bool NOVAC, bool ACCUM>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const int n_near,
+          const TexAll tex) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
-    const Nbr<true> nb(s, tex);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
@@ -255,7 +280,8 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
     const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);
     const double rc2 = g.rc2, inv_dr = tb.inv_dr;
-    const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo;
+    const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo, ns = tex.ns;
+    const cudaTextureObject_t tx = tex.t;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         const int d0 = unit_to_dev(g, u, upp, lane);
         const bool live = d0 >= 0;
@@ -269,53 +295,63 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         if (!SINGLE) d_eli = dir[tic];
         double fx = 0.0, fy = 0.0, fz = 0.0;
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
-#pragma unroll 2
-        for (int q = 0; q < n_off; q++) {
+        auto pair = [&](const double dx, const double dy, const double dz, const double d2, const bool in, const int tj, const int j) {
+            const double recip = rsqrt_fast(d2);
+            const double dfj = tex_f64(tx, j + 3 * ns);
+            const Split sx = split_fast(d2 * recip, inv_dr, n_m1, row_lo);
+            mmin = min(mmin, (NEEDTYPE && !in) ? 0x7fffffff : sx.m0);
+            const HBasis hb = hbasis(sx.p);
+            const HSlope hs = hslope(sx.p);
+            double z2, z2p, emb;
+            double2 r0, r1;
+            if (SINGLE) {
+                rows_s(b_ph0, sx.m, r0, r1);
+                z2 = hval(hb, r0, r1);
+                z2p = hder(hs, r0, r1);
+                rows_s(b_el0, sx.m, r0, r1);
+                emb = hder(hs, r0, r1) * (dfi + dfj);
+            } else {
+                const int tjc = max(tj, 0);
+                rows_g(dir[MISA_MAX_TYPES + tic * MISA_MAX_TYPES + tjc], sx.m, r0, r1);
+                z2 = hval(hb, r0, r1);
+                z2p = hder(hs, r0, r1);
+                rows_g(d_eli, sx.m, r0, r1);
+                const double rho_p_from = hder(hs, r0, r1);
+                double rho_p_to = rho_p_from;
+                if (__any_sync(0xffffffffu, tjc != tic)) {
+                    rows_g(dir[tjc], sx.m, r0, r1);
+                    rho_p_to = hder(hs, r0, r1);
+                }
+                emb = fma(rho_p_from, dfj, rho_p_to * dfi);
+            }
+            double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
+            fp = in ? fp : 0.0;
+            fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
+        };
+EAM_UNROLL(EAM_UNROLL_NEAR)
+        for (int q = 0; q < n_near; q++) {
             const int j = d + off[q];
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
-            const double dx = xi - nb.X(j), dy = yi - nb.Y(j), dz = zi - nb.Z(j);
+            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            pair(dx, dy, dz, d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj, j);
+        }
+EAM_UNROLL(EAM_UNROLL_FAR)
+        for (int q = n_near; q < n_off; q++) {
+            const int j = d + off[q];
+            int tj = 0;
+            if (NEEDTYPE) tj = s.type[j];
+            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
-            if (__any_sync(0xffffffffu, in)) {
-                const double recip = rsqrt_fast(d2);
-                const double dfj = nb.DF(j);
-                const Split sx = split_fast(d2 * recip, inv_dr, n_m1, row_lo);
-                mmin = min(mmin, sx.m0);
-                const HBasis hb = hbasis(sx.p);
-                const HSlope hs = hslope(sx.p);
-                double z2, z2p, emb;
-                double2 r0, r1;
-                if (SINGLE) {
-                    rows_s(b_ph0, sx.m, r0, r1);
-                    z2 = hval(hb, r0, r1);
-                    z2p = hder(hs, r0, r1);
-                    rows_s(b_el0, sx.m, r0, r1);
-                    emb = hder(hs, r0, r1) * (dfi + dfj);
-                } else {
-                    const int tjc = max(tj, 0);
-                    rows_g(dir[MISA_MAX_TYPES + tic * MISA_MAX_TYPES + tjc], sx.m, r0, r1);
-                    z2 = hval(hb, r0, r1);
-                    z2p = hder(hs, r0, r1);
-                    rows_g(d_eli, sx.m, r0, r1);
-                    const double rho_p_from = hder(hs, r0, r1);
-                    double rho_p_to = rho_p_from;
-                    if (__any_sync(0xffffffffu, tjc != tic)) {
-                        rows_g(dir[tjc], sx.m, r0, r1);
-                        rho_p_to = hder(hs, r0, r1);
-                    }
-                    emb = fma(rho_p_from, dfj, rho_p_to * dfi);
-                }
-                double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
-                fp = in ? fp : 0.0;
-                fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
-            }
+            if (__any_sync(0xffffffffu, in)) pair(dx, dy, dz, d2, in, tj, j);
         }
         const bool low = mmin < row_lo;
         if (__any_sync(0xffffffffu, low)) {
             if (low) {
-                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, NEEDTYPE ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types, tb.n_r, inv_dr, rc2,
-                                                  offs + (par ? n_off : 0), n_off, d, tic);
+                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, NEEDTYPE ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types,
+                                                  tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d, tic);
                 fx = f.x; fy = f.y; fz = f.z;
             }
         }

@@ -21,7 +21,9 @@
 #include "ctx.h"
 #include "kernels.cuh"
 
+#ifndef EAM_THREADS
 #define EAM_THREADS 1024
+#endif
 #define EAM_MAX_STAGED 4
 
 struct StagePlan {

@@ -86,7 +86,7 @@ static inline int nblk(long long n) { return (int)((n + MISA_BLOCK - 1) / MISA_B
 // -------------------------------------------------------------------------------------------------
 static int census_local(misa_b200_ctx *c);
 static int census_fetch(misa_b200_ctx *c);
-static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off);
+static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off, int *n_near = nullptr);
 static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes);
 static inline bool no_vacancy(const misa_b200_ctx *c);
 static int smem_kernels_init(int optin) {
@@ -180,13 +180,28 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)g.n_ext;
-    for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.x[k], n)); TRY(dmalloc(&c->s.v[k], n)); TRY(dmalloc(&c->s.f[k], n)); }
-    TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.df, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n));
-    for (int k = 0; k < 3; k++) { CU(cudaMemset(c->s.x[k], 0, n * 8)); CU(cudaMemset(c->s.v[k], 0, n * 8)); CU(cudaMemset(c->s.f[k], 0, n * 8)); }
-    CU(cudaMemset(c->s.rho, 0, n * 8)); CU(cudaMemset(c->s.df, 0, n * 8)); CU(cudaMemset(c->s.type, 0xff, n)); CU(cudaMemset(c->s.id, 0, n * 8));
+    // x, y, z and df -- the fields the stencil kernels gather from neighbours -- share one allocation so that one
+    // texture handle reaches all four (field stride padded to 512 B, the linear-texture base alignment)
+    c->xyzd_stride = (long long)((n + 63) / 64 * 64);
+    TRY(dmalloc(&c->d_xyzd, 4 * (size_t)c->xyzd_stride));
+    CU(cudaMemset(c->d_xyzd, 0, 4 * (size_t)c->xyzd_stride * 8));
+    for (int k = 0; k < 3; k++) c->s.x[k] = c->d_xyzd + (size_t)k * c->xyzd_stride;
+    c->s.df = c->d_xyzd + 3 * (size_t)c->xyzd_stride;
+    for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.v[k], n)); TRY(dmalloc(&c->s.f[k], n)); }
+    TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n));
+    for (int k = 0; k < 3; k++) { CU(cudaMemset(c->s.v[k], 0, n * 8)); CU(cudaMemset(c->s.f[k], 0, n * 8)); }
+    CU(cudaMemset(c->s.rho, 0, n * 8)); CU(cudaMemset(c->s.type, 0xff, n)); CU(cudaMemset(c->s.id, 0, n * 8));
     {
         cudaResourceDesc rd;
         cudaTextureDesc td;
+        memset(&rd, 0, sizeof rd);
+        memset(&td, 0, sizeof td);
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = c->d_xyzd;
+        rd.res.linear.desc = cudaCreateChannelDesc<int2>();
+        rd.res.linear.sizeInBytes = 4 * (size_t)c->xyzd_stride * sizeof(double);
+        td.readMode = cudaReadModeElementType;
+        if (4 * c->xyzd_stride >= (1LL << 31) || cudaCreateTextureObject(&c->tex_all, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); c->tex_all = 0; }
         double *fields[4] = {c->s.x[0], c->s.x[1], c->s.x[2], c->s.df};
         cudaTextureObject_t *objs[4] = {&c->tex_x[0], &c->tex_x[1], &c->tex_x[2], &c->tex_df};
         for (int k = 0; k < 4; k++) {
@@ -268,10 +283,12 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     if (!c) return MISA_B200_OK;
     cudaStreamSynchronize(c->stream);
     misa_b200_comm_destroy(c);
-    for (int k = 0; k < 3; k++) { cudaFree(c->s.x[k]); cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
     for (int k = 0; k < 3; k++) if (c->tex_x[k]) cudaDestroyTextureObject(c->tex_x[k]);
     if (c->tex_df) cudaDestroyTextureObject(c->tex_df);
-    cudaFree(c->s.rho); cudaFree(c->s.df); cudaFree(c->s.type); cudaFree(c->s.id);
+    if (c->tex_all) cudaDestroyTextureObject(c->tex_all);
+    cudaFree(c->d_xyzd);
+    for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
+    cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo);
     cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
@@ -314,8 +331,29 @@ static int upload_offsets(misa_b200_ctx *c) {
         "neighbour offsets: even/odd lists must be non-empty and of equal length");
     c->n_full = (int)c->ref_off[0].size();
     std::vector<int> full(2 * (size_t)c->n_full), levels;
-    for (int p = 0; p < 2; p++)
-        for (int q = 0; q < c->n_full; q++) full[(size_t)p * c->n_full + q] = ref_off_to_dev(c->ref_off[p][q], p, g.H);
+    // device lists are PARTITIONED by site separation (the sums do not depend on the order; the reference order stays
+    // in ref_off for the ABI and the inter-atom kernels): the leading `near` entries -- sites at least 0.1a inside the
+    // cutoff -- are in range for practically every atom and are evaluated without a branch (eam_fast.cuh)
+    std::vector<double> site_r2[2];
+    {
+        const double near_lim = c->dom.cutoff_radius_factor - 0.1;
+        int near[2] = {0, 0};
+        for (int p = 0; p < 2; p++) {
+            std::vector<int> perm(c->n_full);
+            std::vector<double> r2(c->n_full);
+            for (int q = 0; q < c->n_full; q++) { perm[q] = q; r2[q] = off_site_r2(c->ref_off[p][q], p, g); }
+            // near group first; inside a group keep the reference's order (ascending memory offset: consecutive
+            // iterations then touch neighbouring lines, which is what keeps the L1 hit rate up)
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return (r2[a] < near_lim * near_lim) > (r2[b] < near_lim * near_lim); });
+            site_r2[p].resize(c->n_full);
+            for (int q = 0; q < c->n_full; q++) {
+                full[(size_t)p * c->n_full + q] = ref_off_to_dev(c->ref_off[p][perm[q]], p, g.H);
+                site_r2[p][q] = r2[perm[q]];
+                if (site_r2[p][q] < near_lim * near_lim) near[p]++;
+            }
+        }
+        c->near_full = std::min(near[0], near[1]);
+    }
     // pairs of LATTICE atoms can only be within the cutoff if their sites are closer than crf + 2*dmax/a;
     // atom::decide keeps dmax <= 0.2a (reference src/atom.cpp:42), the device measures the actual value.
     for (int L = 0; L < misa_b200_ctx::kLevels; L++) {
@@ -324,9 +362,10 @@ static int upload_offsets(misa_b200_ctx *c) {
         c->level_ofs[L] = levels.size();
         for (int p = 0; p < 2; p++)
             for (int q = 0; q < c->n_full; q++)
-                if (off_site_r2(c->ref_off[p][q], p, g) < lim * lim) { levels.push_back(full[(size_t)p * c->n_full + q]); n[p]++; }
+                if (site_r2[p][q] < lim * lim) { levels.push_back(full[(size_t)p * c->n_full + q]); n[p]++; }
         REQ(n[0] == n[1], MISA_B200_EINVAL, "neighbour offsets: pruned lists differ in length");
         c->level_n[L] = n[0];
+        c->level_near[L] = std::min(c->near_full, n[0]);
     }
     cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
     c->d_off_full = c->d_off_levels = nullptr;
@@ -705,15 +744,17 @@ static inline bool has_inter(const misa_b200_ctx *c) { return c->n_inter_local +
 
 // The offset list the lattice stencil kernels loop: the smallest pruned level that the measured maximum
 // displacement allows, the reference's full list when nothing is known (or pruning is switched off).
-static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off) {
+static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off, int *n_near) {
     offs = c->d_off_full;
     n_off = c->n_full;
+    if (n_near) *n_near = c->near_full;
     if (!c->opt_prune || !c->dmax_valid) return;
     const double d = sqrt(c->dmax2) + 1e-6;
     const int L = (int)ceil(d / (0.01 * c->geo.a));
     if (L >= misa_b200_ctx::kLevels || c->level_n[L] <= 0) return;
     offs = c->d_off_levels + c->level_ofs[L];
     n_off = c->level_n[L];
+    if (n_near) *n_near = c->level_near[L];
 }
 
 // measure dmax over the whole ghost-extended array (positions as they are now, ghosts included)
@@ -811,19 +852,17 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     const int *offs;
-    int n_off;
-    pick_list(c, offs, n_off);
+    int n_off, n_near;
+    pick_list(c, offs, n_off, &n_near);
     const size_t sm = (size_t)n_off * sizeof(int);
     Slot sl(c, MISA_B200_K_RHO);
     StagePlan sp;
     size_t sb;
-    if (c->opt_fast && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df && make_plan(c, sp, sb)) {
+    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb)) {
         const int grid = c->sm_count;
         const bool novac = no_vacancy(c), single = sp.single >= 0;
-        SoaTex tex;
-        for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
-        tex.df = c->tex_df;
-#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+        const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex)
 #define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
         if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
 #undef RHO_FA
@@ -873,20 +912,20 @@ static int launch_force(misa_b200_ctx *c, bool accum) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     const int *offs;
-    int n_off;
-    pick_list(c, offs, n_off);
+    int n_off, n_near;
+    pick_list(c, offs, n_off, &n_near);
     const size_t sm = (size_t)n_off * sizeof(int);
     Slot sl(c, MISA_B200_K_FORCE);
     StagePlan sp;
     size_t sb;
-    if (c->opt_fast && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df && make_plan(c, sp, sb)) {
+    // alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the second
+    // generation's staged/divergent one (1.50 vs 1.18 ms at 97:2:1), so multi-species force stays on k_force_s
+    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
         const int grid = c->sm_count;
         const bool novac = no_vacancy(c), single = sp.single >= 0;
-        SoaTex tex;
-        for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
-        tex.df = c->tex_df;
-#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex); \
-                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex); } while (0)
+        const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex); \
+                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex); } while (0)
         if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
 #undef FORCE_F
         c->launches++;

@@ -8,8 +8,9 @@ from misa_md_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 sigma = float(sys.argv[3]) if len(sys.argv) > 3 else 0.08
+ratio = tuple(int(v) for v in sys.argv[4:7]) if len(sys.argv) > 6 else (1, 0, 0)
 P = (n, n, n)
-st = synth.create_global_state(P)
+st = synth.create_global_state(P, ratio=ratio)
 synth.perturb_positions(st, sigma)
 ctx = mb.Context(P)
 ctx.make_offsets()
