@@ -37,6 +37,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout. Native libraries write there too (NCCL prints its version banner on
+# fd 1 when NCCL_DEBUG is set), so fd 1 is pointed at stderr for the whole run and the line goes to the saved fd.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -180,7 +199,7 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     arm.close()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(budget_s=20.0):
@@ -347,7 +366,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
@@ -364,6 +383,7 @@ def main():
     args = ap.parse_args()
     if args.gpus not in GRIDS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -130,6 +130,14 @@ struct misa_b200_ctx {
     int last_runaways = 0;
     // options
     int opt_prune = 1, opt_fuse = 1;
+    // pipelined step (misa_b200.cu:step_pipelined): ghost exchange on stream2 while interior cells are computed
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_v1 = nullptr, ev_act = nullptr, ev_hx = nullptr, ev_rho = nullptr, ev_hdf = nullptr;
+    unsigned long long *d_stepinfo_g = nullptr; // [0] activity, [1] dmax2 bits: MAX over all sub-boxes (all-reduce result)
+    int opt_pipe = 1;
+    int opt_overlap = 0;                        // multi-GPU: interior/boundary split with the exchange on stream2
+    int opt_reserve = 12;                       // SMs the interior stencil launches leave to the exchange kernels
+    int64_t pipe_steps = 0, pipe_redo = 0;      // steps taken by the pipelined path / of those re-done serially (off-lattice activity)
     // NCCL
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_size = 1;

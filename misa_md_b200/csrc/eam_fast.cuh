@@ -96,6 +96,14 @@ __device__ __forceinline__ void rows_g(const unsigned long long base, const int 
     asm("ld.v2.f64 {%0, %1}, [%2+16];" : "=d"(b.x), "=d"(b.y) : "l"(addr));
 }
 
+__device__ __forceinline__ void rows_ldg(const double2 *__restrict__ tab, const int m, double2 &a, double2 &b) {
+    a = __ldg(tab + m);
+    b = __ldg(tab + m + 1);
+}
+#ifndef EAM_MULTI_GENERIC
+#define EAM_MULTI_GENERIC 0   // 1: per-lane generic pointers (one instruction stream); 0: staged-or-global branch per lane
+#endif
+
 // per-CTA directory of generic table base addresses (biased so that base + 16 m is row m):
 //   [t] elec[t], [MISA_MAX_TYPES + ti * MISA_MAX_TYPES + tj] phi[ti][tj]
 #define EAM_DIR (MISA_MAX_TYPES + MISA_MAX_TYPES * MISA_MAX_TYPES)
@@ -191,27 +199,35 @@ __device__ __forceinline__ double tex_f64(const cudaTextureObject_t t, const int
 // evaluated without any branch (two independent pairs in flight per thread), the rest behind a warp vote.
 template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const int n_near,
-        const TexAll tex) {
+k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
+        const TexAll tex, const RegionList rl, const LevelSel ls) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
+    const int *offs = offs_h;
+    int n_off = n_off_h, n_near = n_near_h;
+    select_list(ls, offs, n_off, n_near);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
-    if (!SINGLE) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
+    if (!SINGLE && EAM_MULTI_GENERIC) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
-    const long long upp = (g.n_cells_owned + 31) / 32;
+    const long long upp = rl.units;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
     const double rc2 = g.rc2, inv_dr = tb.inv_dr;
     const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo, ns = tex.ns;
     const cudaTextureObject_t tx = tex.t;
+    const int maj = sp.staged_id[0];                      // species whose tables are staged (== sp.single when SINGLE)
+    const int nt = tb.n_types; (void)nt;
+    const double2 *__restrict__ g_herm = sp.g_elec[0];
+    const size_t tstride = (size_t)tb.n_r + 1;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
-        const int d0 = unit_to_dev(g, u, upp, lane);
-        const bool live = d0 >= 0;
-        const int d = live ? d0 : unit_to_dev(g, u, upp, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
-        const int ti = s.type[d];
         const int par = u >= upp;
+        const long long up = u - (par ? upp : 0);
+        const int d0 = region_unit_to_dev(g, rl, up, par, lane);
+        const bool live = d0 >= 0;
+        const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
+        const int ti = s.type[d];
         const int *off = s_off + (par ? n_off : 0);
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double acc = 0.0;
@@ -222,7 +238,9 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
             mmin = min(mmin, (NEEDTYPE && !in) ? 0x7fffffff : sx.m0);
             double2 r0, r1;
             if (SINGLE) rows_s(b_el0, sx.m, r0, r1);
-            else rows_g(dir[max(tj, 0)], sx.m, r0, r1);
+            else if (EAM_MULTI_GENERIC) rows_g(dir[max(tj, 0)], sx.m, r0, r1);
+            else if (tj == maj) rows_s(b_el0, sx.m, r0, r1);
+            else rows_ldg(g_herm + (size_t)max(tj, 0) * tstride, sx.m, r0, r1);
             const double v = hval(hbasis(sx.p), r0, r1);
             acc += in ? v : 0.0;
         };
@@ -266,33 +284,41 @@ EAM_UNROLL(EAM_UNROLL_FAR)
 //   fpair = -(1/r) * ( (1/dr) * (z2'_p / r + emb_p) - z2 / r^2 )
 template <bool SINGLE, bool NOVAC, bool ACCUM>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const int n_near,
-          const TexAll tex) {
+k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
+          const TexAll tex, const RegionList rl, const LevelSel ls) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
+    const int *offs = offs_h;
+    int n_off = n_off_h, n_near = n_near_h;
+    select_list(ls, offs, n_off, n_near);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
-    if (!SINGLE) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
+    if (!SINGLE && EAM_MULTI_GENERIC) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
-    const long long upp = (g.n_cells_owned + 31) / 32;
+    const long long upp = rl.units;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
     const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);
     const double rc2 = g.rc2, inv_dr = tb.inv_dr;
     const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo, ns = tex.ns;
     const cudaTextureObject_t tx = tex.t;
+    const int maj = sp.staged_id[0];                      // species whose tables are staged (== sp.single when SINGLE)
+    const int nt = tb.n_types; (void)nt;
+    const double2 *__restrict__ g_herm = sp.g_elec[0];
+    const size_t tstride = (size_t)tb.n_r + 1;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
-        const int d0 = unit_to_dev(g, u, upp, lane);
+        const int par = u >= upp;
+        const long long up = u - (par ? upp : 0);
+        const int d0 = region_unit_to_dev(g, rl, up, par, lane);
         const bool live = d0 >= 0;
-        const int d = live ? d0 : unit_to_dev(g, u, upp, 0);
+        const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);
         const int ti = s.type[d];
         const int tic = max(ti, 0);
-        const int par = u >= upp;
         const int *off = s_off + (par ? n_off : 0);
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         unsigned long long d_eli = 0;
-        if (!SINGLE) d_eli = dir[tic];
+        if (!SINGLE && EAM_MULTI_GENERIC) d_eli = dir[tic];
         double fx = 0.0, fy = 0.0, fz = 0.0;
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
         auto pair = [&](const double dx, const double dy, const double dz, const double d2, const bool in, const int tj, const int j) {
@@ -312,15 +338,33 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
                 emb = hder(hs, r0, r1) * (dfi + dfj);
             } else {
                 const int tjc = max(tj, 0);
-                rows_g(dir[MISA_MAX_TYPES + tic * MISA_MAX_TYPES + tjc], sx.m, r0, r1);
-                z2 = hval(hb, r0, r1);
-                z2p = hder(hs, r0, r1);
-                rows_g(d_eli, sx.m, r0, r1);
-                const double rho_p_from = hder(hs, r0, r1);
-                double rho_p_to = rho_p_from;
-                if (__any_sync(0xffffffffu, tjc != tic)) {
-                    rows_g(dir[tjc], sx.m, r0, r1);
-                    rho_p_to = hder(hs, r0, r1);
+                double rho_p_from, rho_p_to;
+                if (EAM_MULTI_GENERIC) {
+                    rows_g(dir[MISA_MAX_TYPES + tic * MISA_MAX_TYPES + tjc], sx.m, r0, r1);
+                    z2 = hval(hb, r0, r1);
+                    z2p = hder(hs, r0, r1);
+                    rows_g(d_eli, sx.m, r0, r1);
+                    rho_p_from = hder(hs, r0, r1);
+                    rho_p_to = rho_p_from;
+                    if (__any_sync(0xffffffffu, tjc != tic)) {
+                        rows_g(dir[tjc], sx.m, r0, r1);
+                        rho_p_to = hder(hs, r0, r1);
+                    }
+                } else {
+                    const bool mi = tic == maj, mj = tjc == maj;
+                    if (mi && mj) rows_s(b_ph0, sx.m, r0, r1);
+                    else rows_ldg(g_herm + (size_t)(nt + tic * nt + tjc) * tstride, sx.m, r0, r1);
+                    z2 = hval(hb, r0, r1);
+                    z2p = hder(hs, r0, r1);
+                    if (mi) rows_s(b_el0, sx.m, r0, r1);
+                    else rows_ldg(g_herm + (size_t)tic * tstride, sx.m, r0, r1);
+                    rho_p_from = hder(hs, r0, r1);
+                    rho_p_to = rho_p_from;
+                    if (tjc != tic) {
+                        if (mj) rows_s(b_el0, sx.m, r0, r1);
+                        else rows_ldg(g_herm + (size_t)tjc * tstride, sx.m, r0, r1);
+                        rho_p_to = hder(hs, r0, r1);
+                    }
                 }
                 emb = fma(rho_p_from, dfj, rho_p_to * dfi);
             }

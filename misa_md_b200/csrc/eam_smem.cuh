@@ -155,6 +155,41 @@ __device__ __forceinline__ int unit_to_dev(const Geo &g, const long long u, cons
     return owned_cell_to_dev(g, p, c, cx, y, z);
 }
 
+// ---- work regions: a kernel launch covers a list of boxes of owned cells (the whole sub-box, its interior, or the
+//      six boundary slabs), so that interior cells can be computed while the ghost exchange is in flight --------
+#define EAM_MAX_REGIONS 7
+struct Region { int x0, y0, z0, nx, ny, nz; long long u0; };   // u0: first warp unit of this box (within one parity)
+struct RegionList { int n; long long units; Region r[EAM_MAX_REGIONS]; };  // units: warp units per parity
+__device__ __forceinline__ int region_unit_to_dev(const Geo &g, const RegionList &rl, const long long u, const int p, const int lane) {
+    int b = 0;
+    while (b + 1 < rl.n && u >= rl.r[b + 1].u0) b++;
+    const Region &r = rl.r[b];
+    const long long c = (u - r.u0) * 32 + lane;
+    if (c >= (long long)r.nx * r.ny * r.nz) return -1;
+    const int cx = (int)(c % r.nx);
+    const long long t = c / r.nx;
+    const int y = (int)(t % r.ny), z = (int)(t / r.ny);
+    return (int)(p * g.H + ((long long)(z + r.z0 + g.gz) * g.sy + (y + r.y0 + g.gy)) * g.sxc + (cx + r.x0 + g.gx));
+}
+
+// ---- device-side choice of the pruned offset list from the largest displacement measured by k_verlet1 in the
+//      SAME step (no host round trip between the integrator and the stencil kernels; host twin: pick_list) ------
+#define EAM_LEVELS 21
+struct LevelSel {
+    const unsigned long long *dmax2_bits;   // null: use the list the host passed
+    const int *levels, *full;               // d_off_levels, d_off_full
+    int n[EAM_LEVELS], near_[EAM_LEVELS], ofs[EAM_LEVELS];
+    int n_full, near_full;
+    double step;                            // 0.01 a
+};
+__device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs, int &n_off, int &n_near) {
+    if (!ls.dmax2_bits) return;
+    const double d = sqrt(__longlong_as_double((long long)*ls.dmax2_bits)) + 1e-6;
+    const int L = (int)ceil(d / ls.step);
+    if (L < EAM_LEVELS && ls.n[min(L, EAM_LEVELS - 1)] > 0) { offs = ls.levels + ls.ofs[L]; n_off = ls.n[L]; n_near = ls.near_[L]; }
+    else { offs = ls.full; n_off = ls.n_full; n_near = ls.near_full; }
+}
+
 // ---- neighbour field access: plain global loads (LSU pipe) or texture fetches (TEX pipe of the same L1) -----
 struct SoaTex { cudaTextureObject_t x[3], df; };
 template <bool TEX> struct Nbr;
@@ -184,20 +219,24 @@ template <> struct Nbr<true> {
 // NOVAC: the census found no vacant site anywhere (ghosts included), so the per-neighbour type test is dropped.
 template <bool SINGLE, bool FUSE_DF, bool ACCUM, bool TEX = false, bool NOVAC = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const SoaTex tex,
+        const RegionList rl, const LevelSel ls) {
     const Nbr<TEX> nb(s, tex);
+    const int *offs = offs_h;
+    int n_off = n_off_h, n_near_unused = 0;
+    select_list(ls, offs, n_off, n_near_unused);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
-    const long long upp = (g.n_cells_owned + 31) / 32;
+    const long long upp = rl.units;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4); // SINGLE: staged slot 0 = elec[single]
     const int maj = sp.staged_id[0];                 // species whose tables are staged (== sp.single when SINGLE)
     const double2 *g_el0 = sp.g_elec[maj];
     const size_t tstride = (size_t)tb.n_r + 1;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
-        const int d = unit_to_dev(g, u, upp, lane);
+        const int d = region_unit_to_dev(g, rl, u - (u >= upp ? upp : 0), u >= upp, lane);
         if (d < 0) continue;
         const int ti = s.type[d];
         if (ti < 0) {
@@ -231,14 +270,18 @@ k_rho_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
 // ---- K3 force: atom::latForce (reference src/atom.cpp:311-358), full-list gather ---------------------------
 template <bool SINGLE, bool ACCUM, bool TEX = false, bool NOVAC = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
-k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs, const int n_off, const SoaTex tex) {
+k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const SoaTex tex,
+          const RegionList rl, const LevelSel ls) {
     const Nbr<TEX> nb(s, tex);
+    const int *offs = offs_h;
+    int n_off = n_off_h, n_near_unused = 0;
+    select_list(ls, offs, n_off, n_near_unused);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
-    const long long upp = (g.n_cells_owned + 31) / 32;
+    const long long upp = rl.units;
     const int nt = tb.n_types;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);      // SINGLE: slot 0 = elec[single]
     const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);                // SINGLE: slot 1 = phi[single][single]
@@ -247,7 +290,7 @@ k_force_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const double2 *g_ph0 = sp.g_phi[maj * nt + maj];
     const size_t tstride = (size_t)tb.n_r + 1;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
-        const int d = unit_to_dev(g, u, upp, lane);
+        const int d = region_unit_to_dev(g, rl, u - (u >= upp ? upp : 0), u >= upp, lane);
         if (d < 0) continue;
         const int ti = s.type[d];
         if (ti < 0) {

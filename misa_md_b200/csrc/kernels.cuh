@@ -253,53 +253,66 @@ k_verlet2(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
 // ---- K6 halo: LatPacker / DfEmbedPacker (reference src/pack/lat_particle_packer.cpp:153-193,
 //      src/pack/df_embed_packer.cpp:27-68) as device pack / unpack / local periodic copy -------------------
 // message layout for positions: 4 doubles per site {x+shift, y+shift, z+shift, type} (LatParticleData, 32 B)
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_pack_x(const int n, const int *__restrict__ send, const Soa s, const double sx, const double sy, const double sz,
-         double *__restrict__ buf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int d = send[i];
+// Both directions of one exchange stage in ONE launch (the exchange is launch-latency bound: 2.3 MB messages).
+// Entry i < n0 belongs to direction 0, the rest to direction 1; the two directions never touch the same site.
+struct Halo2 {
+    int n0, n1;
+    const int *send0, *send1, *recv0, *recv1;
+    double sh0[3], sh1[3];
+};
+__global__ void __launch_bounds__(MISA_BLOCK) k_pack_x2(const Halo2 h, const Soa s, double *__restrict__ buf0, double *__restrict__ buf1) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.n0 + h.n1) return;
+    const bool hi = i >= h.n0;
+    if (hi) i -= h.n0;
+    const int d = hi ? h.send1[i] : h.send0[i];
+    const double *sh = hi ? h.sh1 : h.sh0;
     double4 r;
-    r.x = __dadd_rn(s.x[0][d], sx);
-    r.y = __dadd_rn(s.x[1][d], sy);
-    r.z = __dadd_rn(s.x[2][d], sz);
+    r.x = __dadd_rn(s.x[0][d], sh[0]);
+    r.y = __dadd_rn(s.x[1][d], sh[1]);
+    r.z = __dadd_rn(s.x[2][d], sh[2]);
     r.w = (double)s.type[d];
-    reinterpret_cast<double4 *>(buf)[i] = r;
+    reinterpret_cast<double4 *>(hi ? buf1 : buf0)[i] = r;
 }
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_unpack_x(const int n, const int *__restrict__ recv, const Soa s, const double *__restrict__ buf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int d = recv[i];
-    const double4 r = reinterpret_cast<const double4 *>(buf)[i];
+__global__ void __launch_bounds__(MISA_BLOCK) k_unpack_x2(const Halo2 h, const Soa s, const double *__restrict__ buf0, const double *__restrict__ buf1) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.n0 + h.n1) return;
+    const bool hi = i >= h.n0;
+    if (hi) i -= h.n0;
+    const int d = hi ? h.recv1[i] : h.recv0[i];
+    const double4 r = reinterpret_cast<const double4 *>(hi ? buf1 : buf0)[i];
     s.x[0][d] = r.x; s.x[1][d] = r.y; s.x[2][d] = r.z;
     s.type[d] = (int8_t)(int)r.w;
 }
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_copy_x(const int n, const int *__restrict__ send, const int *__restrict__ recv, const Soa s, const double sx,
-         const double sy, const double sz) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int a = send[i], b = recv[i];
-    s.x[0][b] = __dadd_rn(s.x[0][a], sx);
-    s.x[1][b] = __dadd_rn(s.x[1][a], sy);
-    s.x[2][b] = __dadd_rn(s.x[2][a], sz);
+__global__ void __launch_bounds__(MISA_BLOCK) k_copy_x2(const Halo2 h, const Soa s) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.n0 + h.n1) return;
+    const bool hi = i >= h.n0;
+    if (hi) i -= h.n0;
+    const int a = hi ? h.send1[i] : h.send0[i], b = hi ? h.recv1[i] : h.recv0[i];
+    const double *sh = hi ? h.sh1 : h.sh0;
+    s.x[0][b] = __dadd_rn(s.x[0][a], sh[0]);
+    s.x[1][b] = __dadd_rn(s.x[1][a], sh[1]);
+    s.x[2][b] = __dadd_rn(s.x[2][a], sh[2]);
     s.type[b] = s.type[a];
 }
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_pack_1(const int n, const int *__restrict__ send, const double *__restrict__ field, double *__restrict__ buf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) buf[i] = field[send[i]];
+__global__ void __launch_bounds__(MISA_BLOCK) k_pack_12(const Halo2 h, const double *__restrict__ field, double *__restrict__ buf0, double *__restrict__ buf1) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.n0 + h.n1) return;
+    if (i < h.n0) buf0[i] = field[h.send0[i]];
+    else buf1[i - h.n0] = field[h.send1[i - h.n0]];
 }
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_unpack_1(const int n, const int *__restrict__ recv, double *__restrict__ field, const double *__restrict__ buf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) field[recv[i]] = buf[i];
+__global__ void __launch_bounds__(MISA_BLOCK) k_unpack_12(const Halo2 h, double *__restrict__ field, const double *__restrict__ buf0, const double *__restrict__ buf1) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.n0 + h.n1) return;
+    if (i < h.n0) field[h.recv0[i]] = buf0[i];
+    else field[h.recv1[i - h.n0]] = buf1[i - h.n0];
 }
-__global__ void __launch_bounds__(MISA_BLOCK)
-k_copy_1(const int n, const int *__restrict__ send, const int *__restrict__ recv, double *__restrict__ field) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) field[recv[i]] = field[send[i]];
+__global__ void __launch_bounds__(MISA_BLOCK) k_copy_12(const Halo2 h, double *__restrict__ field) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h.n0 + h.n1) return;
+    if (i < h.n0) field[h.recv0[i]] = field[h.send0[i]];
+    else field[h.recv1[i - h.n0]] = field[h.send1[i - h.n0]];
 }
 // fused periodic ghost fill for a 1x1x1 process grid: the three staged self-exchanges composed into one map
 __global__ void __launch_bounds__(MISA_BLOCK)

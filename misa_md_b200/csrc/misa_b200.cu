@@ -220,6 +220,10 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     CU(cudaMallocHost((void **)&c->h_counters, 16 * sizeof(int)));
     TRY(dmalloc(&c->d_stepinfo, 4));
     CU(cudaMemset(c->d_stepinfo, 0, 4 * sizeof(unsigned long long)));
+    TRY(dmalloc(&c->d_stepinfo_g, 4));
+    CU(cudaMemset(c->d_stepinfo_g, 0, 4 * sizeof(unsigned long long)));
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&c->ev_v1, &c->ev_act, &c->ev_hx, &c->ev_rho, &c->ev_hdf}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CU(cudaMallocHost((void **)&c->h_stepinfo, 4 * sizeof(unsigned long long)));
     TRY(dmalloc(&c->d_reduce, 8));
     CU(cudaMallocHost((void **)&c->h_reduce, 8 * sizeof(double)));
@@ -275,6 +279,15 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     CU(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     TRY(smem_kernels_init(c->smem_optin));
     misa_b200_set_timestep(c, 0.001);
+    if (const char *env = getenv("MISA_B200_OPTS")) {   // "name=value,name=value": A/B switches for benches (same library, same kernels)
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            const size_t end = std::min(e.find(',', pos), e.size()), eq = e.find('=', pos);
+            if (eq != std::string::npos && eq < end) misa_b200_set_option(c, e.substr(pos, eq - pos).c_str(), atoi(e.substr(eq + 1, end - eq - 1).c_str()));
+            pos = end + 1;
+        }
+    }
     *out = c;
     return MISA_B200_OK;
 }
@@ -290,7 +303,9 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
     cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
-    cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo);
+    cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
     cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
     cudaFree(c->d_census); cudaFreeHost(c->h_census);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
@@ -620,6 +635,9 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "tex")) c->opt_tex = value;
     else if (!strcmp(name, "novac")) c->opt_novac = value;
     else if (!strcmp(name, "fast")) c->opt_fast = value;
+    else if (!strcmp(name, "pipe")) c->opt_pipe = value;
+    else if (!strcmp(name, "reserve")) c->opt_reserve = value;
+    else if (!strcmp(name, "overlap")) c->opt_overlap = value;
     else return fail(MISA_B200_EINVAL, std::string("unknown option ") + name);
     return 0;
 }
@@ -636,6 +654,8 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
     const bool planned = c->have_pot && c->have_off && make_plan(c, sp, sb);
     if (!strcmp(name, "n_off")) *value = n_off;
     else if (!strcmp(name, "n_full")) *value = c->n_full;
+    else if (!strcmp(name, "pipe_steps")) *value = (double)c->pipe_steps;
+    else if (!strcmp(name, "pipe_redo")) *value = (double)c->pipe_redo;
     else if (!strcmp(name, "dmax")) *value = c->dmax_valid ? sqrt(c->dmax2) : -1.0;
     else if (!strcmp(name, "single")) *value = planned ? sp.single : -2;
     else if (!strcmp(name, "novac")) *value = no_vacancy(c) ? 1 : 0;
@@ -672,59 +692,51 @@ extern "C" int misa_b200_comm_destroy(misa_b200_ctx *c) {
 // halo exchange: comm::neiSendReceive<T> forward (x -> y -> z), restated on the device
 // -------------------------------------------------------------------------------------------------
 // width: doubles per site in the message (4 for positions+type, 1 for df)
-static int halo_forward(misa_b200_ctx *c, bool positions) {
+static int halo_forward(misa_b200_ctx *c, bool positions, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
     const int width = positions ? 4 : 1;
     if (c->all_self && c->n_ghost_map > 0) {
         const int n = c->n_ghost_map;
         if (positions)
-            k_ghost_fill_x<<<nblk(n), MISA_BLOCK, 0, c->stream>>>(n, c->d_ghost_dst, c->d_ghost_src, c->d_ghost_shift, c->s,
+            k_ghost_fill_x<<<nblk(n), MISA_BLOCK, 0, st>>>(n, c->d_ghost_dst, c->d_ghost_src, c->d_ghost_shift, c->s,
                                                                  c->dom.meas_global_length[0], c->dom.meas_global_length[1],
                                                                  c->dom.meas_global_length[2]);
         else
-            k_ghost_fill_1<<<nblk(n), MISA_BLOCK, 0, c->stream>>>(n, c->d_ghost_dst, c->d_ghost_src, c->s.df);
+            k_ghost_fill_1<<<nblk(n), MISA_BLOCK, 0, st>>>(n, c->d_ghost_dst, c->d_ghost_src, c->s.df);
         c->launches++;
         CU(cudaGetLastError());
         return 0;
     }
     for (int d = 0; d < 3; d++) {
         const bool self = c->dom.grid_size[d] == 1;
+        const HaloList &h0 = c->halo[d][0], &h1 = c->halo[d][1];
+        Halo2 h;
+        h.n0 = h0.n; h.n1 = h1.n;
+        h.send0 = h0.d_send; h.send1 = h1.d_send; h.recv0 = h0.d_recv; h.recv1 = h1.d_recv;
+        for (int k = 0; k < 3; k++) { h.sh0[k] = h0.shift[k]; h.sh1[k] = h1.shift[k]; }
+        const int nb = nblk(h.n0 + h.n1);
         if (self) {
-            for (int dir = 0; dir < 2; dir++) {
-                const HaloList &h = c->halo[d][dir];
-                if (positions)
-                    k_copy_x<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, h.d_recv, c->s, h.shift[0], h.shift[1], h.shift[2]);
-                else
-                    k_copy_1<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, h.d_recv, c->s.df);
-                c->launches++;
-            }
+            if (positions) k_copy_x2<<<nb, MISA_BLOCK, 0, st>>>(h, c->s);
+            else k_copy_12<<<nb, MISA_BLOCK, 0, st>>>(h, c->s.df);
+            c->launches++;
             CU(cudaGetLastError());
             continue;
         }
         REQ(c->nccl_comm, MISA_B200_ESTATE, "halo exchange across sub-boxes needs misa_b200_comm_init");
-        for (int dir = 0; dir < 2; dir++) {
-            const HaloList &h = c->halo[d][dir];
-            if (positions)
-                k_pack_x<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, c->s, h.shift[0], h.shift[1], h.shift[2], c->d_sendbuf[dir]);
-            else
-                k_pack_1<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_send, c->s.df, c->d_sendbuf[dir]);
-            c->launches++;
-        }
+        if (positions) k_pack_x2<<<nb, MISA_BLOCK, 0, st>>>(h, c->s, c->d_sendbuf[0], c->d_sendbuf[1]);
+        else k_pack_12<<<nb, MISA_BLOCK, 0, st>>>(h, c->s.df, c->d_sendbuf[0], c->d_sendbuf[1]);
+        c->launches++;
         CU(cudaGetLastError());
         NC(g_nccl.GroupStart());
         for (int dir = 0; dir < 2; dir++) {
-            const HaloList &h = c->halo[d][dir];
-            NC(g_nccl.Send(c->d_sendbuf[dir], (size_t)h.n * width, kNcclDouble, c->dom.rank_id_neighbours[d][dir], c->nccl_comm, c->stream));
-            NC(g_nccl.Recv(c->d_recvbuf[dir], (size_t)h.n * width, kNcclDouble, c->dom.rank_id_neighbours[d][(dir + 1) % 2], c->nccl_comm, c->stream));
+            const HaloList &hl = c->halo[d][dir];
+            NC(g_nccl.Send(c->d_sendbuf[dir], (size_t)hl.n * width, kNcclDouble, c->dom.rank_id_neighbours[d][dir], c->nccl_comm, st));
+            NC(g_nccl.Recv(c->d_recvbuf[dir], (size_t)hl.n * width, kNcclDouble, c->dom.rank_id_neighbours[d][(dir + 1) % 2], c->nccl_comm, st));
         }
         NC(g_nccl.GroupEnd());
-        for (int dir = 0; dir < 2; dir++) {
-            const HaloList &h = c->halo[d][dir];
-            if (positions)
-                k_unpack_x<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_recv, c->s, c->d_recvbuf[dir]);
-            else
-                k_unpack_1<<<nblk(h.n), MISA_BLOCK, 0, c->stream>>>(h.n, h.d_recv, c->s.df, c->d_recvbuf[dir]);
-            c->launches++;
-        }
+        if (positions) k_unpack_x2<<<nb, MISA_BLOCK, 0, st>>>(h, c->s, c->d_recvbuf[0], c->d_recvbuf[1]);
+        else k_unpack_12<<<nb, MISA_BLOCK, 0, st>>>(h, c->s.df, c->d_recvbuf[0], c->d_recvbuf[1]);
+        c->launches++;
         CU(cudaGetLastError());
     }
     return 0;
@@ -848,7 +860,44 @@ static inline bool no_vacancy(const misa_b200_ctx *c) {
     return c->opt_novac && c->n_valid_sites == c->geo.n_ext && !c->seen_offlattice;
 }
 
-static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
+// whole sub-box / interior (no ghost site within the stencil reach) / the six boundary slabs around it
+static RegionList make_regions(const Geo &g, int which) {
+    RegionList rl;
+    memset(&rl, 0, sizeof rl);
+    auto add = [&](int x0, int y0, int z0, int nx, int ny, int nz) {
+        if (nx <= 0 || ny <= 0 || nz <= 0) return;
+        Region &r = rl.r[rl.n++];
+        r.x0 = x0; r.y0 = y0; r.z0 = z0; r.nx = nx; r.ny = ny; r.nz = nz; r.u0 = rl.units;
+        rl.units += ((long long)nx * ny * nz + 31) / 32;
+    };
+    const bool has_interior = g.nx > 2 * g.gx && g.ny > 2 * g.gy && g.nz > 2 * g.gz;
+    if (which == 0 || !has_interior) { if (which != 1) add(0, 0, 0, g.nx, g.ny, g.nz); return rl; }
+    const int ix = g.nx - 2 * g.gx, iy = g.ny - 2 * g.gy, iz = g.nz - 2 * g.gz;
+    if (which == 1) { add(g.gx, g.gy, g.gz, ix, iy, iz); return rl; }
+    add(0, 0, 0, g.nx, g.ny, g.gz); add(0, 0, g.nz - g.gz, g.nx, g.ny, g.gz);
+    add(0, 0, g.gz, g.nx, g.gy, iz); add(0, g.ny - g.gy, g.gz, g.nx, g.gy, iz);
+    add(0, g.gy, g.gz, g.gx, iy, iz); add(g.nx - g.gx, g.gy, g.gz, g.gx, iy, iz);
+    return rl;
+}
+// dmax2: device word holding the bit pattern of the largest squared displacement (null: the host's pick_list choice)
+static LevelSel make_levelsel(const misa_b200_ctx *c, const unsigned long long *dmax2) {
+    LevelSel ls;
+    memset(&ls, 0, sizeof ls);
+    if (!dmax2 || !c->opt_prune) return ls;
+    ls.dmax2_bits = dmax2;
+    ls.levels = c->d_off_levels; ls.full = c->d_off_full;
+    for (int L = 0; L < misa_b200_ctx::kLevels; L++) { ls.n[L] = c->level_n[L]; ls.near_[L] = c->level_near[L]; ls.ofs[L] = (int)c->level_ofs[L]; }
+    ls.n_full = c->n_full; ls.near_full = c->near_full;
+    ls.step = 0.01 * c->geo.a;
+    return ls;
+}
+struct StencilOpt {                 // how one stencil launch deviates from "whole sub-box, host-chosen list, main stream"
+    int region = 0;                 // 0 whole, 1 interior, 2 boundary slabs
+    const unsigned long long *dmax2 = nullptr;
+    int reserve_sms = 0;            // leave this many SMs free (the persistent CTAs would otherwise starve the exchange kernels on stream2)
+};
+
+static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilOpt &so = StencilOpt()) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     const int *offs;
@@ -859,10 +908,13 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
     StagePlan sp;
     size_t sb;
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb)) {
-        const int grid = c->sm_count;
+        const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex)
+        const RegionList rl = make_regions(g, so.region);
+        const LevelSel ls = make_levelsel(c, so.dmax2);
+        if (rl.units == 0) return 0;
+#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls)
 #define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
         if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
 #undef RHO_FA
@@ -872,19 +924,22 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum) {
         return 0;
     }
     if (make_plan(c, sp, sb)) {
-        const int grid = c->sm_count;
+        const int grid = std::max(1, c->sm_count - so.reserve_sms);
         SoaTex tex;
         for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
         tex.df = c->tex_df;
         const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
         const bool novac = no_vacancy(c);
-#define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
-#define RHO_X(T, N) k_rho_s<true, true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+        const RegionList rl = make_regions(g, so.region);
+        const LevelSel ls = make_levelsel(c, so.dmax2);
+        if (rl.units == 0) return 0;
+#define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
+#define RHO_X(T, N) k_rho_s<true, true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
         if (sp.single >= 0 && fuse_df && !accum && (use_tex || novac)) {
             if (use_tex && novac) RHO_X(true, true); else if (use_tex) RHO_X(true, false); else RHO_X(false, true);
         } else
         if (sp.single < 0 && fuse_df && !accum && use_tex)
-            k_rho_s<false, true, false, true, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex);
+            k_rho_s<false, true, false, true, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls);
         else
         if (sp.single >= 0) { if (accum) RHO_S(true, false, true); else if (fuse_df) RHO_S(true, true, false); else RHO_S(true, false, false); }
         else { if (accum) RHO_S(false, false, true); else if (fuse_df) RHO_S(false, true, false); else RHO_S(false, false, false); }
@@ -908,7 +963,7 @@ static int launch_df(misa_b200_ctx *c) {
     CU(cudaGetLastError());
     return 0;
 }
-static int launch_force(misa_b200_ctx *c, bool accum) {
+static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = StencilOpt()) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     const int *offs;
@@ -921,11 +976,14 @@ static int launch_force(misa_b200_ctx *c, bool accum) {
     // alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the second
     // generation's staged/divergent one (1.50 vs 1.18 ms at 97:2:1), so multi-species force stays on k_force_s
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
-        const int grid = c->sm_count;
+        const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex); \
-                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex); } while (0)
+        const RegionList rl = make_regions(g, so.region);
+        const LevelSel ls = make_levelsel(c, so.dmax2);
+        if (rl.units == 0) return 0;
+#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls); \
+                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls); } while (0)
         if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
 #undef FORCE_F
         c->launches++;
@@ -933,19 +991,22 @@ static int launch_force(misa_b200_ctx *c, bool accum) {
         return 0;
     }
     if (make_plan(c, sp, sb)) {
-        const int grid = c->sm_count;
+        const int grid = std::max(1, c->sm_count - so.reserve_sms);
         SoaTex tex;
         for (int k = 0; k < 3; k++) tex.x[k] = c->tex_x[k];
         tex.df = c->tex_df;
         const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
         const bool novac = no_vacancy(c);
-#define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
-#define FORCE_X(T, N) k_force_s<true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex)
+        const RegionList rl = make_regions(g, so.region);
+        const LevelSel ls = make_levelsel(c, so.dmax2);
+        if (rl.units == 0) return 0;
+#define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
+#define FORCE_X(T, N) k_force_s<true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
         if (sp.single >= 0 && !accum && (use_tex || novac)) {
             if (use_tex && novac) FORCE_X(true, true); else if (use_tex) FORCE_X(true, false); else FORCE_X(false, true);
         } else
         if (sp.single < 0 && !accum && use_tex)
-            k_force_s<false, false, true, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex);
+            k_force_s<false, false, true, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls);
         else
         if (sp.single >= 0) { if (accum) FORCE_S(true, true); else FORCE_S(true, false); }
         else { if (accum) FORCE_S(false, true); else FORCE_S(false, false); }
@@ -987,35 +1048,43 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
 
 // Agree across all sub-boxes whether any off-lattice atom exists this step (the list exchanges are collective
 // between neighbours, so every rank must take the same branch); also brings the step counters to the host.
-static int update_activity(misa_b200_ctx *c) {
-    k_activity<<<1, 1, 0, c->stream>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost, c->d_stepinfo);
+// Enqueued on `st`; the results are in h_counters / h_stepinfo once `st` (or ev_act) has been waited for, and in
+// d_stepinfo_g on the device (kernels of the same step read the global dmax from there).
+static int activity_enqueue(misa_b200_ctx *c, cudaStream_t st) {
+    k_activity<<<1, 1, 0, st>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost, c->d_stepinfo);
     c->launches++;
     if (c->comm_size > 1 && c->nccl_comm) // [0] activity, [1] dmax2 bit pattern: MAX over the sub-boxes
-        NC(g_nccl.AllReduce(c->d_stepinfo, c->d_stepinfo, 2, kNcclUint64, kNcclMax, c->nccl_comm, c->stream));
-    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, 10 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(c->h_stepinfo, c->d_stepinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        NC(g_nccl.AllReduce(c->d_stepinfo, c->d_stepinfo_g, 2, kNcclUint64, kNcclMax, c->nccl_comm, st));
+    else
+        CU(cudaMemcpyAsync(c->d_stepinfo_g, c->d_stepinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, 10 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_stepinfo, c->d_stepinfo_g, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+static int update_activity(misa_b200_ctx *c) {
+    TRY(activity_enqueue(c, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->inter_active = c->h_stepinfo[0] > 0;
     if (c->inter_active) c->seen_offlattice = true;
     return 0;
 }
 
-// NewtonMotion::firststep + atom::decide (+ exchangeInter / borderInter when off-lattice atoms exist)
-extern "C" int misa_b200_pass_verlet1(misa_b200_ctx *c) {
-    TRY(ready(c));
+// NewtonMotion::firststep + the displacement test of atom::decide, enqueued on the main stream
+static int verlet1_enqueue(misa_b200_ctx *c) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     const VerletPar vp = verlet_par(c);
-    if (c->n_inter_local > 0) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_first_step(c, vp)); }
-    {
-        Slot sl(c, MISA_B200_K_VERLET1);
-        CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
-        CU(cudaMemsetAsync(c->d_stepinfo, 0, 2 * sizeof(unsigned long long), c->stream));
-        k_verlet1<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
-        c->launches++;
-        CU(cudaGetLastError());
-    }
-    TRY(update_activity(c));
+    Slot sl(c, MISA_B200_K_VERLET1);
+    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->d_stepinfo, 0, 2 * sizeof(unsigned long long), c->stream));
+    k_verlet1<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+// ... and what the host does once the step's counters are known: the rest of atom::decide and the inter-atom
+// exchanges when anything is off-lattice anywhere (reference src/atom.cpp:21-84, src/atom/inter_atom_list.cpp:19-53)
+static int verlet1_finish(misa_b200_ctx *c) {
     REQ(c->h_counters[3] == 0, MISA_B200_EOVERFLOW, "run-away list overflow");
     c->last_runaways = c->h_counters[0];
     // k_verlet1 measured every owned atom after the drift and the reduction took the MAX over all sub-boxes, so
@@ -1032,6 +1101,16 @@ extern "C" int misa_b200_pass_verlet1(misa_b200_ctx *c) {
         inter_drop_ghosts(c);
     }
     return 0;
+}
+
+// NewtonMotion::firststep + atom::decide (+ exchangeInter / borderInter when off-lattice atoms exist)
+extern "C" int misa_b200_pass_verlet1(misa_b200_ctx *c) {
+    TRY(ready(c));
+    const VerletPar vp = verlet_par(c);
+    if (c->n_inter_local > 0) { Slot sl(c, MISA_B200_K_INTER); TRY(inter_first_step(c, vp)); }
+    TRY(verlet1_enqueue(c));
+    TRY(update_activity(c));
+    return verlet1_finish(c);
 }
 
 extern "C" int misa_b200_pass_verlet2(misa_b200_ctx *c) {
@@ -1083,9 +1162,87 @@ extern "C" int misa_b200_prepare(misa_b200_ctx *c) {
     return 0;
 }
 
+// One step of the thermal (no off-lattice atom) case without a host round trip on the critical path, with the ghost
+// exchange overlapped with interior-cell compute (the north-star's halo/compute overlap):
+//   main  : verlet1 | rho(interior)            | rho(boundary) | force(interior)         | force(boundary) | verlet2
+//   stream2:        | activity, halo_x (NCCL)  |               | halo_df (NCCL)          |
+// The stencil kernels pick their pruned offset list on the device from the displacement k_verlet1 just measured
+// (interior: this sub-box's own maximum -- every neighbour is owned; boundary: the all-reduced one). The host only
+// looks at the step's activity word right before verlet2 -- it has long arrived by then -- and, if a run-away
+// turned up anywhere, discards the speculative rho/force (they only wrote rho, df, f) and redoes the step serially
+// through the off-lattice path. With a 1x1x1 grid the "exchange" is the periodic ghost fill and runs in line.
+static bool pipe_ok(const misa_b200_ctx *c) {
+    StagePlan sp;
+    size_t sb;
+    return c->opt_pipe && c->opt_fast && c->opt_prune && c->opt_fuse && c->tex_all && !c->prof_on && !has_inter(c) && !c->inter_active &&
+           c->stream2 && make_plan(c, sp, sb);
+}
+static int step_pipelined(misa_b200_ctx *c, bool &redone) {
+    redone = false;
+    // the interior/boundary split only pays when the exchange is long against the compute it hides behind; at 100^3
+    // cells per GPU it is launch-latency bound (about 0.1 ms of 1.5) and the split costs more than it hides
+    // (DESIGN.md section 5), so it is opt-in ("overlap") and the default keeps everything in line on one stream
+    const bool overlap = (!c->all_self && c->opt_overlap) || c->opt_overlap > 1;   // 2: force the split on a 1x1x1 grid too (tests)
+    TRY(verlet1_enqueue(c));
+    StencilOpt whole, interior, boundary;
+    whole.dmax2 = c->d_stepinfo_g + 1;
+    interior.region = 1; interior.dmax2 = c->d_stepinfo + 1; interior.reserve_sms = c->opt_reserve;
+    boundary.region = 2; boundary.dmax2 = c->d_stepinfo_g + 1;
+    if (!overlap) {
+        TRY(activity_enqueue(c, c->stream));
+        CU(cudaEventRecord(c->ev_act, c->stream));
+        TRY(halo_forward(c, true));
+        TRY(launch_rho(c, true, false, whole));
+        TRY(halo_forward(c, false));
+        TRY(launch_force(c, false, whole));
+    } else {
+        CU(cudaEventRecord(c->ev_v1, c->stream));
+        CU(cudaStreamWaitEvent(c->stream2, c->ev_v1, 0));
+        TRY(activity_enqueue(c, c->stream2));
+        CU(cudaEventRecord(c->ev_act, c->stream2));
+        TRY(halo_forward(c, true, c->stream2));
+        CU(cudaEventRecord(c->ev_hx, c->stream2));
+        TRY(launch_rho(c, true, false, interior));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_hx, 0));
+        TRY(launch_rho(c, true, false, boundary));
+        CU(cudaEventRecord(c->ev_rho, c->stream));
+        CU(cudaStreamWaitEvent(c->stream2, c->ev_rho, 0));
+        TRY(halo_forward(c, false, c->stream2));
+        CU(cudaEventRecord(c->ev_hdf, c->stream2));
+        TRY(launch_force(c, false, interior));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_hdf, 0));
+        TRY(launch_force(c, false, boundary));
+    }
+    CU(cudaEventSynchronize(c->ev_act));
+    c->inter_active = c->h_stepinfo[0] > 0;
+    c->pipe_steps++;
+    if (c->inter_active || c->h_counters[3] != 0) {
+        // off-lattice activity somewhere: x and v are as verlet1 left them (rho/force never touch them), so the
+        // serial path can take over from exactly there
+        c->seen_offlattice = true;
+        c->pipe_redo++;
+        redone = true;
+        CU(cudaStreamSynchronize(c->stream2));
+        CU(cudaStreamSynchronize(c->stream));
+        TRY(verlet1_finish(c));
+        TRY(misa_b200_pass_halo_x(c));
+        if (!c->dmax_valid) TRY(measure_displacement(c));
+        if (has_inter(c)) TRY(inter_clear(c));
+        TRY(compute_eam(c));
+    } else {
+        TRY(verlet1_finish(c));
+    }
+    return misa_b200_pass_verlet2(c);
+}
+
 extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
     TRY(ready(c));
     for (int s = 0; s < n_steps; s++) {
+        if (pipe_ok(c)) {
+            bool redone;
+            TRY(step_pipelined(c, redone));
+            continue;
+        }
         TRY(misa_b200_pass_verlet1(c));
         TRY(misa_b200_pass_halo_x(c));
         if (!c->dmax_valid) TRY(measure_displacement(c));

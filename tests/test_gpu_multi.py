@@ -14,8 +14,10 @@ torch = pytest.importorskip("torch")
 import torch.multiprocessing as mp
 
 
-def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka):
+def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka, opts=""):
     os.environ.setdefault("NCCL_DEBUG", "WARN")
+    if opts:
+        os.environ["MISA_B200_OPTS"] = opts
     lib = mb.load()
     mb.capi._ck(lib.misa_b200_env_init(rank))
     coord = (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
@@ -43,11 +45,11 @@ def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka):
     ctx.close()
 
 
-def _run(tmp_path, phase, grid, ratio, steps, pka=None):
+def _run(tmp_path, phase, grid, ratio, steps, pka=None, opts=""):
     world = grid[0] * grid[1] * grid[2]
     if mb.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    mp.spawn(_worker, args=(world, phase, grid, ratio, steps, str(tmp_path), pka), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, phase, grid, ratio, steps, str(tmp_path), pka, opts), nprocs=world, join=True)
     st = cm.make_state(phase, ratio=ratio, sigma=0.03)
     w = cm.oracle_world(st, grid=grid, dt=pka["dt"] if pka else 0.001, threads=world)
     w.prepare()
@@ -78,6 +80,15 @@ def _compare(tmp_path, w, xtol, ftol):
 
 def test_two_gpus_track_oracle(tmp_path):
     w = _run(tmp_path, (12, 8, 8), (2, 1, 1), (90, 6, 4), steps=5)
+    _compare(tmp_path, w, 1e-12, 1e-9)
+    w.close()
+
+
+@pytest.mark.parametrize("opts", ["pipe=0", "pipe=1,overlap=1,reserve=8"])
+def test_two_gpus_serial_and_overlapped_exchange(tmp_path, opts):
+    """The serial step and the interior/boundary split with the NCCL exchange on a second stream (sub-boxes of
+    8x8x8 cells: a 2x2x2 interior) both track the oracle."""
+    w = _run(tmp_path, (16, 8, 8), (2, 1, 1), (90, 6, 4), steps=5, opts=opts)
     _compare(tmp_path, w, 1e-12, 1e-9)
     w.close()
 

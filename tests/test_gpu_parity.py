@@ -101,6 +101,75 @@ def test_kernel_variants_match_oracle(tex, novac):
         w.close()
 
 
+@pytest.mark.parametrize("ratio", [(1, 0, 0), (90, 6, 4)])
+def test_kernel_generations_agree(ratio):
+    """Third-generation kernels (eam_fast.cuh: warp-uniform range test, Hermite basis form, near/far lists) against
+    the second generation (eam_smem.cuh) and the oracle on the same state."""
+    st = cm.make_state((9, 10, 11), ratio=ratio, sigma=0.07)
+    w = cm.oracle_world(st)
+    w.prepare()
+    ref = None
+    out = {}
+    for fast in (0, 1, 2):   # 2: also the multi-species force of generation three
+        ctx = cm.gpu_context(st)
+        ctx.set_option("fast", fast)
+        ctx.prepare()
+        out[fast] = cm.owned(ctx, ctx.download())
+        if ref is None:
+            ref = cm.owned(ctx, w.atoms(0))
+        ctx.close()
+    for fast in (0, 1, 2):
+        assert cm.rel_err(out[fast]["rho"], ref["rho"]) < TOL
+        assert cm.rel_err(out[fast]["df"], ref["df"]) < TOL
+        assert cm.rel_err(out[fast]["f"], ref["f"]) < 1e-9
+    assert cm.rel_err(out[1]["f"], out[0]["f"]) < 1e-11
+    assert cm.rel_err(out[2]["f"], out[0]["f"]) < 1e-11
+    w.close()
+
+
+@pytest.mark.parametrize("ratio", [(1, 0, 0), (90, 6, 4)])
+def test_pipelined_step_is_the_serial_step(ratio):
+    """The sync-free step (device-side choice of the pruned list, activity word checked before verlet2) and its
+    interior / boundary split must reproduce the serial step BIT FOR BIT: same kernels, same lists, same order of
+    the per-atom sums."""
+    st = cm.make_state((11, 10, 12), ratio=ratio, sigma=0.02)
+    out = {}
+    for name, opts in (("serial", {"pipe": 0}), ("pipe", {"pipe": 1}), ("split", {"pipe": 1, "overlap": 2, "reserve": 8})):
+        ctx = cm.gpu_context(st)
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.prepare()
+        ctx.step(6)
+        out[name] = cm.owned(ctx, ctx.download())
+        if name != "serial":
+            assert ctx.query("pipe_steps") == 6 and ctx.query("pipe_redo") == 0
+        ctx.close()
+    for name in ("pipe", "split"):
+        for fld in ("type", "x", "v", "f", "rho", "df"):
+            assert np.array_equal(out[name][fld], out["serial"][fld]), (name, fld)
+
+
+def test_pipelined_step_falls_back_on_runaway():
+    """A PKA makes atoms leave their sites: the speculative rho/force of that step are discarded and the step is
+    redone through the off-lattice path, so the trajectory equals the serial one exactly."""
+    st = cm.make_state((10, 10, 10))
+    out = {}
+    for pipe in (0, 1):
+        ctx = cm.gpu_context(st, dt=2e-4)
+        ctx.set_option("pipe", pipe)
+        ctx.prepare()
+        ctx.collision_step((5, 5, 5, 0), (3.0, 0.7, 0.4), 400.0)
+        ctx.step(60)
+        out[pipe] = (cm.owned(ctx, ctx.download()), ctx.download_inter())
+        if pipe:
+            assert ctx.query("pipe_redo") >= 1
+        ctx.close()
+    assert len(out[0][1]) > 0
+    assert np.array_equal(out[0][1]["id"], out[1][1]["id"])
+    for fld in ("type", "x", "v", "f"):
+        assert np.array_equal(out[0][0][fld], out[1][0][fld]), fld
+
+
 def test_close_pairs_below_staged_range():
     """Pairs closer than the staged r range (r < 2 Angstrom) take the global Hermite rows: same results."""
     st = cm.make_state((8, 8, 8), sigma=0.0)
