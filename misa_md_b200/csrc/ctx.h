@@ -135,8 +135,8 @@ struct misa_b200_ctx {
     cudaEvent_t ev_v1 = nullptr, ev_act = nullptr, ev_hx = nullptr, ev_rho = nullptr, ev_hdf = nullptr;
     unsigned long long *d_stepinfo_g = nullptr; // [0] activity, [1] dmax2 bits: MAX over all sub-boxes (all-reduce result)
     int opt_pipe = 1;
-    int opt_overlap = 0;                        // multi-GPU: interior/boundary split with the exchange on stream2
-    int opt_reserve = 12;                       // SMs the interior stencil launches leave to the exchange kernels
+    int opt_overlap = -1;                       // multi-GPU: interior/boundary split with the exchange on stream2 (-1 auto)
+    int opt_reserve = 8;                        // SMs the interior stencil launches leave to the exchange kernels
     int64_t pipe_steps = 0, pipe_redo = 0;      // steps taken by the pipelined path / of those re-done serially (off-lattice activity)
     // NCCL
     void *nccl_comm = nullptr;

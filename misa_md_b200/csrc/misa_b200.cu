@@ -1179,10 +1179,14 @@ static bool pipe_ok(const misa_b200_ctx *c) {
 }
 static int step_pipelined(misa_b200_ctx *c, bool &redone) {
     redone = false;
-    // the interior/boundary split only pays when the exchange is long against the compute it hides behind; at 100^3
-    // cells per GPU it is launch-latency bound (about 0.1 ms of 1.5) and the split costs more than it hides
-    // (DESIGN.md section 5), so it is opt-in ("overlap") and the default keeps everything in line on one stream
-    const bool overlap = (!c->all_self && c->opt_overlap) || c->opt_overlap > 1;   // 2: force the split on a 1x1x1 grid too (tests)
+    // The interior/boundary split pays when the exchange is long against what it costs (8 SMs left to the exchange
+    // kernels + two extra launches): measured on B200, 100^3 cells per GPU -- 2x1x1 grid (one NCCL stage, 0.11 ms of
+    // exchange): 1.50 ms in line vs 1.59 ms split; 2x2x2 grid (three stages, 0.38 ms): 1.81 ms in line vs 1.61 ms
+    // split. "overlap": -1 auto (split when at least two dimensions exchange over NCCL), 0 never, 1 whenever any
+    // dimension does, 2 always (tests: also on a 1x1x1 grid).
+    int nccl_dims = 0;
+    for (int d = 0; d < 3; d++) nccl_dims += c->dom.grid_size[d] > 1;
+    const bool overlap = c->opt_overlap > 1 || (c->opt_overlap == 1 && nccl_dims >= 1) || (c->opt_overlap < 0 && nccl_dims >= 2);
     TRY(verlet1_enqueue(c));
     StencilOpt whole, interior, boundary;
     whole.dmax2 = c->d_stepinfo_g + 1;
