@@ -132,11 +132,38 @@ int misa_b200_step(misa_b200_ctx *ctx, int n_steps); /* firststep .. secondstep,
 int misa_b200_step_host(misa_b200_ctx *ctx, void *atoms, int n_steps);
 int misa_b200_setv(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy); /* atom::setv */
 int misa_b200_collision_step(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy);
-int misa_b200_rescale(misa_b200_ctx *ctx, double t_set, double n_atoms_global); /* configuration::rescale (single rank sums; see thermo) */
+/* configuration::rescale's velocity scaling (reference src/system_configuration.cpp:97-110) with the CURRENT global
+ * temperature supplied by the caller: v *= sqrt(t_set / t_now) on this sub-box (lattice + inter list) */
+int misa_b200_rescale(misa_b200_ctx *ctx, double t_set, double t_now);
 /* thermo[0]=sum m v^2 (configuration::mvv), [1]=E_pot local [eV] (ours), [2]=owned valid atoms,
  * [3]=local inter atoms, [4]=ghost inter atoms, [5]=run-aways detected in the last step */
 int misa_b200_thermo(misa_b200_ctx *ctx, double out[6]);
 int misa_b200_sync(misa_b200_ctx *ctx);
+
+/* ---- the callers / data formats either side of the path, resident mode ------------------ */
+/* WorldBuilder::build (reference src/world_builder.cpp:64-199) on the device, BY GLOBAL ATOM ID: ids, species,
+ * perfect bcc positions, velocities (std::mt19937(seed)() / 0xFFFFFFFF - 0.5) / mass with draw 3(id-1)+k for
+ * component k of atom id (what the reference produces on one rank; independent of the process grid), vcm +
+ * zeroMomentum over the global box, configuration::rescale to t_set (0: no rescale). A single non-zero ratio
+ * gives a pure lattice; otherwise species = cumulative-ratio rule on a counter-based hash of (alloy_seed, id)
+ * (the reference's unseeded rand() has no reproducible stream). Collective only in the sense that every rank
+ * must call it with the same arguments; no communication. Replaces misa_b200_upload_atoms for synthetic starts. */
+int misa_b200_build_world(misa_b200_ctx *ctx, uint32_t seed, double t_set, const int32_t ratio[3], uint64_t alloy_seed);
+/* configuration::temperature / kineticEnergy (reference src/system_configuration.cpp:26-64) over ALL sub-boxes
+ * (one NCCL all-reduce when a communicator is set): out[0] = sum m v^2, [1] = T [K] with dof = 3 n - 3,
+ * [2] = kinetic energy [eV], [3] = atoms counted (lattice + inter). Every rank must call it. */
+int misa_b200_temperature(misa_b200_ctx *ctx, uint64_t n_atoms_global, double out[4]);
+/* configuration::rescale (reference src/system_configuration.cpp:86-111), global: temperature as above, then
+ * v *= sqrt(t_set / T) on the device. The stage machine's `rescale` (frontend/md_simulation.cpp:62-66). */
+int misa_b200_rescale_to(misa_b200_ctx *ctx, double t_set, uint64_t n_atoms_global);
+/* AtomDump::dump + BufferedFileWriter::write (reference frontend/io/atom_dump.cpp:39-75, frontend/io/
+ * buffered_io.cpp:18-36): the 72-byte atom_dump::AtomInfoDump record stream (frontend/io/atom_info_dump.h:14-22;
+ * id, step, type, inter_type = 0, location, velocity; padding bytes zero) of this sub-box -- inter atoms in list
+ * order, then the valid sites of [begin, end) (ghost-inclusive doubled-x coordinates; NULL = the owned sub-box of
+ * frontend/io/output_base_interface.h:26-31) in z,y,x order -- compacted on the device; only the records cross
+ * PCIe. records == NULL: size query. n_records always receives the record count. */
+int misa_b200_dump_records(misa_b200_ctx *ctx, const int32_t begin[3], const int32_t end[3], uint64_t time_step,
+                           void *records, size_t cap_records, size_t *n_records);
 
 /* single passes on the resident state (kernel-level parity tests and profiling) */
 int misa_b200_pass_halo_x(misa_b200_ctx *ctx);  /* AtomList::exchangeAtom */

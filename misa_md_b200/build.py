@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmisa_b200.so")
 SOURCES = ["misa_b200.cu"]
-DEPS = ["misa_b200.cu", "kernels.cuh", "inter.cuh", "eam_smem.cuh", "ctx.h", "util.cuh", "nccl_dl.cuh", "../../include/misa_b200.h"]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + ["../../include/misa_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false",

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .synth import ATOM_DTYPE
+from .synth import ATOM_DTYPE, DUMP_DTYPE
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 K_NAMES = ["verlet1", "halo_x", "rho", "df", "halo_df", "force", "verlet2", "inter", "xfer"]
@@ -30,6 +30,7 @@ EXPORTS = [
     "misa_b200_pass_force", "misa_b200_pass_verlet1", "misa_b200_pass_verlet2", "misa_b200_set_option", "misa_b200_query",
     "misa_b200_comm_unique_id", "misa_b200_comm_init", "misa_b200_comm_destroy",
     "misa_b200_profile_enable", "misa_b200_profile_read", "misa_b200_launch_count", "misa_b200_timed_steps",
+    "misa_b200_build_world", "misa_b200_temperature", "misa_b200_rescale_to", "misa_b200_dump_records",
 ]
 
 
@@ -112,6 +113,10 @@ def load(build=True):
     L.misa_b200_profile_read.argtypes = [vp, C.POINTER(d * K_COUNT), C.POINTER(C.c_int64 * K_COUNT)]
     L.misa_b200_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     L.misa_b200_timed_steps.argtypes = [vp, i, C.POINTER(d)]
+    L.misa_b200_build_world.argtypes = [vp, C.c_uint32, d, C.POINTER(C.c_int32 * 3), C.c_uint64]
+    L.misa_b200_temperature.argtypes = [vp, C.c_uint64, C.POINTER(d * 4)]
+    L.misa_b200_rescale_to.argtypes = [vp, d, C.c_uint64]
+    L.misa_b200_dump_records.argtypes = [vp, C.POINTER(C.c_int32 * 3), C.POINTER(C.c_int32 * 3), C.c_uint64, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L
 
@@ -319,6 +324,34 @@ class Context:
 
     def sync(self):
         _ck(self.L.misa_b200_sync(self.h))
+
+    # ---- callers / data formats either side of the path ----------------------
+    def build_world(self, seed=466953, t_set=600.0, ratio=(1, 0, 0), alloy_seed=1024):
+        _ck(self.L.misa_b200_build_world(self.h, seed, t_set, (C.c_int32 * 3)(*ratio), alloy_seed))
+
+    def n_atoms_global(self):
+        p = self.dom.phase_space
+        return 2 * p[0] * p[1] * p[2]
+
+    def temperature(self):
+        out = (C.c_double * 4)()
+        _ck(self.L.misa_b200_temperature(self.h, self.n_atoms_global(), C.byref(out)))
+        return dict(mvv=out[0], T=out[1], ke=out[2], n_atoms=out[3])
+
+    def rescale_to(self, t_set):
+        _ck(self.L.misa_b200_rescale_to(self.h, t_set, self.n_atoms_global()))
+
+    def dump_records(self, time_step, begin=None, end=None, out=None):
+        """AtomDump::dump record stream (numpy array of DUMP_DTYPE), compacted on the device."""
+        b = C.byref((C.c_int32 * 3)(*begin)) if begin is not None else None
+        e = C.byref((C.c_int32 * 3)(*end)) if end is not None else None
+        n = C.c_size_t()
+        if out is None:
+            _ck(self.L.misa_b200_dump_records(self.h, b, e, time_step, None, 0, C.byref(n)))
+            out = np.zeros(n.value, dtype=DUMP_DTYPE)
+        assert out.dtype == DUMP_DTYPE and out.flags["C_CONTIGUOUS"]
+        _ck(self.L.misa_b200_dump_records(self.h, b, e, time_step, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value]
 
     def run_pass(self, name):
         _ck(getattr(self.L, "misa_b200_pass_" + name)(self.h))

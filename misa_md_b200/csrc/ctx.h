@@ -138,6 +138,10 @@ struct misa_b200_ctx {
     int opt_overlap = -1;                       // multi-GPU: interior/boundary split with the exchange on stream2 (-1 auto)
     int opt_reserve = 8;                        // SMs the interior stencil launches leave to the exchange kernels
     int64_t pipe_steps = 0, pipe_redo = 0;      // steps taken by the pipelined path / of those re-done serially (off-lattice activity)
+    // dump compaction (dump.cuh)
+    unsigned long long *d_dump = nullptr, *d_dump_base = nullptr, *d_dump_total = nullptr, *h_dump_total = nullptr;
+    unsigned *d_dump_count = nullptr;
+    size_t dump_cap = 0, dump_tiles_cap = 0;
     // NCCL
     void *nccl_comm = nullptr;
     int comm_rank = 0, comm_size = 1;

@@ -18,6 +18,8 @@
 #include "inter.cuh"
 #include "eam_smem.cuh"
 #include "eam_fast.cuh"
+#include "dump.cuh"
+#include "world.cuh"
 
 extern "C" const char *misa_b200_last_error(void) { return g_err.c_str(); }
 
@@ -312,6 +314,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
+    cudaFree(c->d_dump); cudaFree(c->d_dump_base); cudaFree(c->d_dump_total); cudaFree(c->d_dump_count); cudaFreeHost(c->h_dump_total);
     inter_free(c);
     for (int k = 0; k < MISA_B200_K_COUNT; k++) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -1409,6 +1412,205 @@ extern "C" int misa_b200_upload_inter(misa_b200_ctx *c, const void *inter_atoms,
 extern "C" int misa_b200_download_inter(misa_b200_ctx *c, void *inter_atoms, size_t cap, size_t *n) {
     REQ(c && n, MISA_B200_EINVAL, "null argument");
     return inter_download(c, inter_atoms, cap, n);
+}
+
+// -------------------------------------------------------------------------------------------------
+// initial state on the device, by global atom id: WorldBuilder::build (reference src/world_builder.cpp:64-103)
+// -------------------------------------------------------------------------------------------------
+extern "C" int misa_b200_build_world(misa_b200_ctx *c, uint32_t seed, double t_set, const int32_t ratio[3], uint64_t alloy_seed) {
+    REQ(c && ratio, MISA_B200_EINVAL, "misa_b200_build_world: null argument");
+    const Geo &g = c->geo;
+    WorldPar w;
+    w.px = c->dom.phase_space[0]; w.py = c->dom.phase_space[1]; w.pz = c->dom.phase_space[2];
+    w.n_global = 2 * w.px * w.py * w.pz;
+    w.ratio_total = 0;
+    w.single = -1;
+    int nonzero = 0;
+    for (int i = 0; i < MISA_MAX_TYPES; i++) {
+        REQ(ratio[i] >= 0, MISA_B200_EINVAL, "misa_b200_build_world: negative alloy ratio");
+        w.ratio[i] = ratio[i];
+        w.ratio_total += ratio[i];
+        w.mass[i] = kMass[i];
+        if (ratio[i] > 0) { nonzero++; w.single = i; }
+    }
+    REQ(w.ratio_total > 0, MISA_B200_EINVAL, "misa_b200_build_world: alloy ratio sums to zero");
+    if (nonzero != 1) w.single = -1;
+    w.alloy_seed = alloy_seed;
+    w.a = c->dom.lattice_const;
+    // the global mt19937 stream: draw 3(id-1)+k is velocity component k of atom id (= the reference on ONE rank)
+    unsigned *d_draws = nullptr;
+    double *d_part = nullptr, *d_out = nullptr;
+    const int nb = (int)std::min<long long>((w.n_global + MISA_BLOCK - 1) / MISA_BLOCK, (long long)std::max(c->sm_count, 1) * 8);
+    CU(cudaMalloc((void **)&d_draws, (size_t)w.n_global * 3 * sizeof(unsigned)));
+    int rc = 0;
+    double h[5] = {0, 0, 0, 0, 0};
+    do {
+        if ((rc = dmalloc(&d_part, (size_t)nb * 4))) break;
+        if ((rc = dmalloc(&d_out, 5))) break;
+        k_mt19937_stream<<<1, 256, 0, c->stream>>>(seed, 3 * w.n_global, d_draws);
+        k_world_moments<<<nb, MISA_BLOCK, 0, c->stream>>>(w, d_draws, d_part);
+        k_sum_partials<4><<<1, MISA_BLOCK, 0, c->stream>>>(d_part, nb, d_out);
+        c->launches += 3;
+        if (cudaMemcpyAsync(h, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = -1; break; }
+        double vcm[3] = {h[0], h[1], h[2]};
+        if (h[3] > 0.0) for (int k = 0; k < 3; k++) vcm[k] /= (double)w.n_global;   // world_builder.cpp:84-88
+        double factor = 1.0;
+        if (t_set != 0.0) {                                                          // :96-101 -> configuration::rescale
+            k_world_mvv<<<nb, MISA_BLOCK, 0, c->stream>>>(w, d_draws, vcm[0], vcm[1], vcm[2], d_part);
+            k_sum_partials<1><<<1, MISA_BLOCK, 0, c->stream>>>(d_part, nb, d_out + 4);
+            c->launches += 2;
+            if (cudaMemcpyAsync(h + 4, d_out + 4, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = -1; break; }
+            const unsigned long long dof = 3ull * (unsigned long long)w.n_global - 3ull;
+            const double scalar = h[4] * kMvv2e / (dof * kBoltz);                    // configuration::temperature, system_configuration.cpp:56-64
+            factor = sqrt(t_set / scalar);                                           // :97
+        }
+        k_world_fill<<<nblk(g.n_ext), MISA_BLOCK, 0, c->stream>>>(g, c->s, w, d_draws, vcm[0], vcm[1], vcm[2], factor);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = -1; break; }
+    } while (0);
+    cudaFree(d_draws); cudaFree(d_part); cudaFree(d_out);
+    if (rc == -1) return fail(MISA_B200_ENODEV, std::string("misa_b200_build_world: ") + cudaGetErrorString(cudaGetLastError()));
+    TRY(rc);
+    TRY(inter_upload(c, nullptr, 0));
+    TRY(census_local(c));
+    TRY(census_fetch(c));
+    c->have_atoms = true;
+    c->dmax_valid = false;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// global thermo / rescale (stage machine): configuration::temperature, kineticEnergy, rescale
+// (reference src/system_configuration.cpp:26-111), summed over ALL sub-boxes with one NCCL all-reduce
+// -------------------------------------------------------------------------------------------------
+static int global_mvv(misa_b200_ctx *c, double sums[2]) {
+    const Geo &g = c->geo;
+    const int bpp = nblk(g.n_cells_owned);
+    double *d_part = nullptr;
+    TRY(dmalloc(&d_part, (size_t)2 * bpp * 2));
+    k_mvv<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, kMass[0], kMass[1], kMass[2], bpp, d_part);
+    k_sum_partials<2><<<1, MISA_BLOCK, 0, c->stream>>>(d_part, 2 * bpp, c->d_reduce);
+    c->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_reduce, c->d_reduce, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_part);
+    CU(e);
+    double mvv = c->h_reduce[0], n = c->h_reduce[1];
+    for (const HostAtom &a : IH(c)->local) {   // inter list after the lattice, list order (system_configuration.cpp:73-82)
+        mvv += (a.v[0] * a.v[0] + a.v[1] * a.v[1] + a.v[2] * a.v[2]) * kMass[a.type];
+        n += 1.0;
+    }
+    if (c->comm_size > 1) {
+        REQ(c->nccl_comm, MISA_B200_ESTATE, "global thermo: communicator not initialised");
+        c->h_reduce[0] = mvv; c->h_reduce[1] = n;
+        CU(cudaMemcpyAsync(c->d_reduce, c->h_reduce, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllReduce(c->d_reduce, c->d_reduce, 2, kNcclDouble, kNcclSum, c->nccl_comm, c->stream));
+        CU(cudaMemcpyAsync(c->h_reduce, c->d_reduce, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        mvv = c->h_reduce[0]; n = c->h_reduce[1];
+    }
+    sums[0] = mvv; sums[1] = n;
+    return 0;
+}
+extern "C" int misa_b200_temperature(misa_b200_ctx *c, uint64_t n_atoms_global, double out[4]) {
+    REQ(c && out, MISA_B200_EINVAL, "misa_b200_temperature: null argument");
+    REQ(c->have_atoms, MISA_B200_ESTATE, "misa_b200_temperature: no atoms on the device");
+    REQ(n_atoms_global > 1, MISA_B200_EINVAL, "misa_b200_temperature: needs more than one atom");
+    double sums[2];
+    TRY(global_mvv(c, sums));
+    const unsigned long long dof = 3ull * n_atoms_global - 3ull;
+    out[0] = sums[0];
+    out[1] = sums[0] * kMvv2e / (dof * kBoltz);  // configuration::temperature, system_configuration.cpp:56-64
+    out[2] = 0.5 * sums[0] * kMvv2e;             // kinetic energy [eV]
+    out[3] = sums[1];
+    return 0;
+}
+extern "C" int misa_b200_rescale_to(misa_b200_ctx *c, double t_set, uint64_t n_atoms_global) {
+    double th[4];
+    TRY(misa_b200_temperature(c, n_atoms_global, th));
+    REQ(th[1] > 0, MISA_B200_ESTATE, "misa_b200_rescale_to: current temperature is zero");
+    return misa_b200_rescale(c, t_set, th[1]);   // v *= sqrt(T / scalar), system_configuration.cpp:97-110
+}
+
+// -------------------------------------------------------------------------------------------------
+// dump record stream: AtomDump::dump + BufferedFileWriter::write (reference frontend/io/atom_dump.cpp:39-75,
+// frontend/io/buffered_io.cpp:18-36), compacted on the device (dump.cuh)
+// -------------------------------------------------------------------------------------------------
+struct DumpRecord { // atom_dump::AtomInfoDump, reference frontend/io/atom_info_dump.h:14-22
+    unsigned long long id, step;
+    int type;
+    short inter_type, _pad;
+    double x[3], v[3];
+};
+static_assert(sizeof(DumpRecord) == 72, "AtomInfoDump layout");
+
+extern "C" int misa_b200_dump_records(misa_b200_ctx *c, const int32_t begin[3], const int32_t end[3], uint64_t time_step,
+                                      void *records, size_t cap_records, size_t *n_records) {
+    REQ(c && n_records, MISA_B200_EINVAL, "misa_b200_dump_records: null argument");
+    REQ(c->have_atoms, MISA_B200_ESTATE, "misa_b200_dump_records: no atoms on the device");
+    const Geo &g = c->geo;
+    DumpRegion r;
+    if (begin && end) {
+        REQ(begin[0] >= 0 && begin[1] >= 0 && begin[2] >= 0 && end[0] <= 2 * g.sxc && end[1] <= g.sy && end[2] <= g.sz &&
+                begin[0] <= end[0] && begin[1] <= end[1] && begin[2] <= end[2],
+            MISA_B200_EINVAL, "misa_b200_dump_records: region outside the ghost-extended lattice");
+        r = {begin[0], begin[1], begin[2], end[0] - begin[0], end[1] - begin[1], end[2] - begin[2], 0};
+    } else { // OutputBaseInterface, reference frontend/io/output_base_interface.h:26-31: the owned sub-box
+        r = {2 * g.gx, g.gy, g.gz, 2 * g.nx, g.ny, g.nz, 0};
+    }
+    r.n = (long long)r.nx * r.ny * r.nz;
+    const size_t n_inter = IH(c)->local.size();
+    const int n_tiles = (int)((r.n + DUMP_TILE - 1) / DUMP_TILE);
+    if (!c->d_dump_total) {
+        TRY(dmalloc(&c->d_dump_total, 1));
+        CU(cudaMallocHost((void **)&c->h_dump_total, sizeof(unsigned long long)));
+    }
+    if ((size_t)n_tiles > c->dump_tiles_cap) {
+        cudaFree(c->d_dump_count); cudaFree(c->d_dump_base);
+        c->d_dump_count = nullptr; c->d_dump_base = nullptr; c->dump_tiles_cap = 0;
+        TRY(dmalloc(&c->d_dump_count, (size_t)n_tiles));
+        TRY(dmalloc(&c->d_dump_base, (size_t)n_tiles));
+        c->dump_tiles_cap = (size_t)n_tiles;
+    }
+    unsigned long long n_lat = 0;
+    if (n_tiles > 0) {
+        k_dump_count<<<n_tiles, DUMP_TILE, 0, c->stream>>>(g, r, c->s.type, c->d_dump_count);
+        k_dump_scan<<<1, 1024, 0, c->stream>>>(c->d_dump_count, c->d_dump_base, n_tiles, c->d_dump_total);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->h_dump_total, c->d_dump_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        n_lat = *c->h_dump_total;
+    }
+    *n_records = n_inter + (size_t)n_lat;
+    if (!records) return 0; // size query
+    REQ(cap_records >= *n_records, MISA_B200_EINVAL, "misa_b200_dump_records: record buffer too small");
+    DumpRecord *out = static_cast<DumpRecord *>(records);
+    for (size_t i = 0; i < n_inter; i++) { // inter atoms first, list order (atom_dump.cpp:59-61)
+        const HostAtom &a = IH(c)->local[i];
+        DumpRecord rec;
+        memset(&rec, 0, sizeof rec);
+        rec.id = a.id; rec.step = time_step; rec.type = a.type; rec.inter_type = 0;
+        for (int d = 0; d < 3; d++) { rec.x[d] = a.x[d]; rec.v[d] = a.v[d]; }
+        out[i] = rec;
+    }
+    if (n_lat == 0) return 0;
+    if ((size_t)n_lat > c->dump_cap) {
+        cudaFree(c->d_dump);
+        c->d_dump = nullptr; c->dump_cap = 0;
+        TRY(dmalloc(&c->d_dump, (size_t)r.n * DUMP_WORDS)); // the whole region: later dumps never reallocate
+        c->dump_cap = (size_t)r.n;
+    }
+    {
+        Slot sl(c, MISA_B200_K_XFER);
+        k_dump_write<<<n_tiles, DUMP_TILE, 0, c->stream>>>(g, r, c->s, c->d_dump_base, (unsigned long long)time_step, c->d_dump);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out + n_inter, c->d_dump, (size_t)n_lat * sizeof(DumpRecord), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 // -------------------------------------------------------------------------------------------------

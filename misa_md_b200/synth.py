@@ -21,12 +21,34 @@ ATOM_DTYPE = np.dtype(
      ("rho", "<f8"), ("df", "<f8")]
 )
 
+# 72-byte dump record atom_dump::AtomInfoDump, reference frontend/io/atom_info_dump.h:14-22
+DUMP_DTYPE = np.dtype(
+    [("id", "<u8"), ("step", "<u8"), ("type", "<i4"), ("inter_type", "<i2"), ("_pad", "<i2"), ("x", "<f8", 3), ("v", "<f8", 3)]
+)
+
 
 def mt19937_unit(seed, n):
     """n draws of md_rand::random(): std::mt19937(seed)() * (1.0 / 0xFFFFFFFF)."""
     bg = np.random.MT19937()
     bg._legacy_seeding(int(seed))
     return bg.random_raw(n).astype(np.float64) * (1.0 / 4294967295.0)
+
+
+def species_by_id(ids, ratio, alloy_seed):
+    """Species of global atom ids (1-based): counter-based hash of (alloy_seed, id) into the cumulative-ratio rule of
+    WorldBuilder::randomAtomsType (reference src/world_builder.cpp:180-199, whose unseeded libc rand() has no
+    reproducible stream). Host mirror of misa_md_b200/csrc/world.cuh:species_by_id -- same integers, bit for bit."""
+    ratio = np.asarray(ratio, dtype=np.int64)
+    ids = np.asarray(ids, dtype=np.uint64)
+    if np.count_nonzero(ratio) == 1:
+        return np.full(ids.shape, int(np.argmax(ratio)), dtype=np.int32)
+    with np.errstate(over="ignore"):
+        z = np.uint64(alloy_seed) + ids * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    draw = ((z >> np.uint64(33)) % np.uint64(int(ratio.sum()))).astype(np.int64)
+    return np.searchsorted(np.cumsum(ratio), draw, side="right").astype(np.int32)
 
 
 def create_global_state(phase_space, a=2.85532, seed=466953, t_set=600.0, ratio=(1, 0, 0), alloy_seed=1024):
@@ -41,15 +63,7 @@ def create_global_state(phase_space, a=2.85532, seed=466953, t_set=600.0, ratio=
     x[..., 1] = j * a + (i % 2) * (a / 2)
     x[..., 2] = k * a + (i % 2) * (a / 2)
     ids = (1 + (k * py + j) * (2 * px) + i).astype(np.uint64)
-    ratio = np.asarray(ratio, dtype=np.int64)
-    if np.count_nonzero(ratio) == 1:
-        types = np.full(shape, int(np.argmax(ratio)), dtype=np.int32)
-    else:
-        # reference uses unseeded libc rand() % total (world_builder.cpp:180-199); a fixed-seed generator
-        # replaces it, same cumulative-ratio rule.
-        rs = np.random.RandomState(alloy_seed)
-        draw = rs.randint(0, int(ratio.sum()), size=n)
-        types = np.searchsorted(np.cumsum(ratio), draw, side="right").astype(np.int32).reshape(shape)
+    types = species_by_id(ids, ratio, alloy_seed)
     mass = MASS[types]
     u = mt19937_unit(seed, 3 * n).reshape(shape + (3,))
     v = (u - 0.5) / mass[..., None]

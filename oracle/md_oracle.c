@@ -1137,3 +1137,43 @@ double ora_potential_energy(ora_world *w) {
     }
     return total;
 }
+
+/* ---- dump record stream ---------------------------------------------------------------------------- */
+/* BufferedFileWriter::write, reference frontend/io/buffered_io.cpp:18-36 (the buffering itself does not change
+ * the byte stream: full buffers and the final flush are written back to back) */
+static void dump_one(const ora_atom *a, size_t time_step, ora_dump_record *out, size_t cap, size_t *n) {
+    if (*n < cap) {
+        ora_dump_record *r = out + *n;
+        memset(r, 0, sizeof *r);
+        r->id = a->id;
+        r->step = time_step;
+        r->type = a->type;
+        r->inter_type = 0; /* normal */
+        for (int d = 0; d < 3; d++) {
+            r->atom_location[d] = a->x[d];
+            r->atom_velocity[d] = a->v[d];
+        }
+    }
+    (*n)++;
+}
+
+/* AtomDump::dump, reference frontend/io/atom_dump.cpp:39-75 */
+size_t ora_dump(const ora_rank *rk, size_t time_step, ora_dump_record *out, size_t cap) {
+    const ora_domain *d = &rk->dom;
+    size_t n = 0;
+    /* region of OutputBaseInterface, reference frontend/io/output_base_interface.h:26-31 */
+    const int b0 = d->dbx_sub_box_lattice_region.x_low - d->dbx_ghost_ext_lattice_region.x_low;
+    const int b1 = d->dbx_sub_box_lattice_region.y_low - d->dbx_ghost_ext_lattice_region.y_low;
+    const int b2 = d->dbx_sub_box_lattice_region.z_low - d->dbx_ghost_ext_lattice_region.z_low;
+    const int e0 = b0 + d->dbx_sub_box_lattice_size[0], e1 = b1 + d->dbx_sub_box_lattice_size[1], e2 = b2 + d->dbx_sub_box_lattice_size[2];
+    for (size_t i = 0; i < rk->n_inter; i++) /* :59-61 inter atoms first, list order */
+        dump_one(&rk->inter[i], time_step, out, cap, &n);
+    for (int k = b2; k < e2; k++)           /* :63-72 */
+        for (int j = b1; j < e1; j++)
+            for (int i = b0; i < e0; i++) {
+                const ora_atom *a = &rk->atoms[((long)k * rk->size_y + j) * rk->size_x + i]; /* getAtomEleByGhostIndex */
+                if (a->type == ORA_INVALID) continue;
+                dump_one(a, time_step, out, cap, &n);
+            }
+    return n;
+}

@@ -165,6 +165,23 @@ size_t ora_rank_n_inter(const ora_rank *rk);
 ora_atom *ora_rank_inter(ora_rank *rk);
 size_t ora_rank_n_ghost_inter(const ora_rank *rk);
 
+/* ---- dump record stream ------------------------------------------------------------------ */
+/* atom_dump::AtomInfoDump, reference frontend/io/atom_info_dump.h:14-22 -- 72 bytes:
+ * id@0 step@8 type@16 inter_type@20 (short; 2 pad bytes, zero here) atom_location@24 atom_velocity@48 */
+typedef struct ora_dump_record {
+    unsigned long id;
+    size_t step;
+    int type;
+    short inter_type;
+    short _pad;
+    double atom_location[3];
+    double atom_velocity[3];
+} ora_dump_record;
+/* AtomDump::dump of one sub-box (reference frontend/io/atom_dump.cpp:39-75): inter atoms in list order, then the
+ * valid sites of the owned region (frontend/io/output_base_interface.h:26-31) in z,y,x order. Returns the record
+ * count; records beyond `cap` are not written. */
+size_t ora_dump(const ora_rank *rk, size_t time_step, ora_dump_record *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -232,3 +232,14 @@ class World:
 
     def total_inter(self):
         return self.L.ora_total_inter(self.h)
+
+    def dump(self, r, time_step):
+        """AtomDump::dump record stream of rank r (numpy array of DUMP_DTYPE)."""
+        from misa_md_b200.synth import DUMP_DTYPE
+        self.L.ora_dump.restype = C.c_size_t
+        self.L.ora_dump.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        rk = self.L.ora_world_rank(self.h, r)
+        n = self.L.ora_dump(rk, time_step, None, 0)
+        out = np.zeros(n, dtype=DUMP_DTYPE)
+        self.L.ora_dump(rk, time_step, out.ctypes.data, n)
+        return out

@@ -79,6 +79,8 @@ def lib(hooks=False):
     L.ref_rescale.argtypes = [vp, d]
     L.ref_is_out_box.argtypes = [vp, i, C.POINTER(d * 3)]
     L.ref_is_out_box.restype = C.c_uint
+    L.ref_dump.argtypes = [vp, i, C.c_size_t, vp, C.c_size_t]
+    L.ref_dump.restype = C.c_size_t
     L.ref_near_lat_sub_box_coord.argtypes = [vp, i, C.POINTER(d * 3), C.POINTER(l * 3)]
     _libs[hooks] = L
     return L
@@ -174,3 +176,14 @@ class World:
 
     def rescale(self, t):
         self.L.ref_rescale(self.h, t)
+
+    def dump(self, r, time_step):
+        """Byte stream AtomDump::dump hands to the file writer for rank r, as DUMP_DTYPE records. The two padding
+        bytes of each record are uninitialised heap in the reference (new AtomInfoDump[]): zeroed here."""
+        from misa_md_b200.synth import DUMP_DTYPE
+        nbytes = self.L.ref_dump(self.h, r, time_step, None, 0)
+        assert nbytes % DUMP_DTYPE.itemsize == 0
+        out = np.zeros(nbytes // DUMP_DTYPE.itemsize, dtype=DUMP_DTYPE)
+        self.L.ref_dump(self.h, r, time_step, out.ctypes.data, nbytes)
+        out["_pad"] = 0
+        return out

@@ -14,6 +14,13 @@ typedef long MPI_Aint;
 #define MPI_DOUBLE 2
 #define MPI_UNSIGNED_LONG 3
 #define MPI_SUM 0
+#define MPI_BYTE 4
+// MPI-IO names used by the reference's dump path (frontend/io/atom_dump.cpp); the file is a memory sink here
+typedef void *MPI_File;
+typedef int MPI_Info;
+#define MPI_INFO_NULL 0
+#define MPI_MODE_CREATE 1
+#define MPI_MODE_WRONLY 4
 extern "C" {
 double MPI_Wtime();
 int MPI_Abort(MPI_Comm comm, int code);
@@ -24,5 +31,7 @@ int MPI_Type_create_struct(int count, const int *blocklengths, const MPI_Aint *d
                            MPI_Datatype *newtype);
 int MPI_Type_commit(MPI_Datatype *type);
 int MPI_Type_free(MPI_Datatype *type);
+int MPI_File_open(MPI_Comm comm, const char *filename, int amode, MPI_Info info, MPI_File *fh);
+int MPI_File_close(MPI_File *fh);
 }
 #endif

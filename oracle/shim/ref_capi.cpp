@@ -78,6 +78,9 @@ public:
     static std::vector<std::vector<_type_atom_id>> &recvlist(AtomList *l) { return l->recvlist; }
 };
 
+size_t ref_dump_rank(AtomList *atom_list, InterAtomList *inter_list, const comm::BccDomain *d, size_t time_step,
+                     unsigned char *out, size_t cap); // ref_dump.cpp
+
 struct RefRank {
     comm::BccDomain *dom = nullptr;
     atom *at = nullptr;
@@ -338,6 +341,13 @@ void ref_rescale(void *h, double T) {
     const comm::BccDomain *d = w->ranks[0].dom;
     const _type_atom_count n_atoms = 2ul * d->phase_space[0] * d->phase_space[1] * d->phase_space[2];
     run_all(w, [&](int r) { configuration::rescale(T, n_atoms, w->ranks[r].at->getAtomList(), w->ranks[r].at->getInterList()); });
+}
+
+// AtomDump::dump of one sub-box at `time_step` (the reference's own frontend/io sources, see ref_dump.cpp):
+// returns the number of bytes of the 72-byte record stream, copied to `out` when it fits
+size_t ref_dump(void *h, int r, size_t time_step, void *out, size_t cap) {
+    RefRank &rk = static_cast<RefWorld *>(h)->ranks[r];
+    return ref_dump_rank(rk.at->getAtomList(), rk.at->getInterList(), rk.dom, time_step, static_cast<unsigned char *>(out), cap);
 }
 
 // ws::* (reference src/lattice/ws_utils.cpp) on a free-standing position

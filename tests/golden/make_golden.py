@@ -16,6 +16,8 @@ them from a generator.
   thermal_2ranks.npz  12x6x6 cells cut 2x1x1: both sub-boxes after prepare() and after 4 steps
   pka.npz             10^3 cells Fe, setv at [5,5,5,0] direction [1,3,5] 400 eV, dt 2e-4: lattice + inter-atom list
                       after 150 steps (4 inter atoms) (atom::setv/decide/interRho/interForce, src/atom.cpp:21-84,194-494)
+                      + the AtomDump::dump byte stream of that state (frontend/io/atom_dump.cpp:39-75)
+  world.npz           WorldBuilder::build on one rank, 6x7x8 cells Fe, seed 466953, 600 K (src/world_builder.cpp:64-199)
   index.npz           NeighbourIndex offsets (src/atom/neighbour_index.inl:13-76) and sendlist/recvlist
                       (src/atom/atom_list.cpp:33-40, src/pack/lat_particle_packer.cpp:65-139) of a 7x8x9 sub-box
 """
@@ -94,8 +96,24 @@ def pka():
     for f in FIELDS:
         out["inter_%s" % f] = inter[f].copy()
     assert inter.size > 0, "the PKA golden must exercise the inter-atom path"
+    # AtomDump::dump of the end state, the reference's own frontend/io sources (oracle/shim/ref_dump.cpp)
+    out["dump_step"] = 150
+    out["dump_bytes"] = np.frombuffer(w.dump(0, 150).tobytes(), dtype=np.uint8)
     w.close()
     np.savez_compressed(os.path.join(HERE, "pka.npz"), **out)
+
+
+def world():
+    """WorldBuilder::build on one rank (reference src/world_builder.cpp:64-199): pure Fe, seed 466953, 600 K."""
+    phase = (6, 7, 8)
+    w = ref_py.World(phase, a=cm.A, crf=cm.CRF)
+    w.build_world(seed=466953, t_set=600.0, ratio=(1, 0, 0))
+    got = w.atoms(0).reshape(w.shape(0))[w.owned_slices(0)]
+    out = {"phase_space": np.array(phase), "seed": 466953, "t_set": 600.0, "temperature": w.temperature()}
+    for f in ("id", "type", "x", "v"):
+        out[f] = got[f].copy()
+    w.close()
+    np.savez_compressed(os.path.join(HERE, "world.npz"), **out)
 
 
 def index():
@@ -119,6 +137,7 @@ if __name__ == "__main__":
     thermal_alloy()
     thermal_2ranks()
     pka()
+    world()
     index()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

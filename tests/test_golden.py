@@ -149,3 +149,56 @@ def test_gpu_pka_golden():
     assert np.array_equal(inter["type"], g["inter_type"])
     assert cm.rel_err(inter["x"], g["inter_x"]) < 1e-8
     ctx.close()
+
+
+# --------------------------------------------------------------------- dump record stream / world builder (8f)
+def test_oracle_dump_reproduces_reference_byte_stream():
+    """ora_dump (restatement of AtomDump::dump + BufferedFileWriter::write) against the byte stream the reference's
+    own frontend/io sources produced for the PKA end state (4 inter atoms, 4 vacancies)."""
+    g = load("pka.npz")
+    w = O.World(tuple(g["phase_space"]), a=cm.A, crf=cm.CRF, dt=float(g["dt"]))
+    w.atoms(0)[:] = aos(g, "end")
+    inter = aos(g, "inter")
+    w.L.ora_test_set_inter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    w.L.ora_test_set_inter(w.h, 0, inter.ctypes.data, len(inter))
+    rec = w.dump(0, int(g["dump_step"]))
+    assert rec.size == 2000 and rec.dtype.itemsize == 72
+    assert rec.tobytes() == g["dump_bytes"].tobytes()
+    assert np.array_equal(rec["id"][:len(inter)], inter["id"])  # inter atoms first, list order
+    w.close()
+
+
+def test_host_world_mirror_matches_reference_world_builder():
+    """synth.create_global_state (host mirror of csrc/world.cuh) against the stored output of the reference's
+    WorldBuilder::build: ids, species, positions exact; velocities to summation rounding."""
+    g = load("world.npz")
+    st = synth.create_global_state(tuple(g["phase_space"]), seed=int(g["seed"]), t_set=float(g["t_set"]))
+    assert np.array_equal(st["id"], g["id"])
+    assert np.array_equal(st["type"], g["type"])
+    assert np.array_equal(st["x"], g["x"])
+    assert np.allclose(st["v"], g["v"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_gpu_dump_golden():
+    g = load("pka.npz")
+    ctx = gpu_ctx(g, prefix="end")
+    ctx.upload_inter(aos(g, "inter"))
+    rec = ctx.dump_records(int(g["dump_step"]))
+    assert rec.tobytes() == g["dump_bytes"].tobytes()   # byte work: identical, padding included
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_build_world_golden():
+    import misa_md_b200 as mb
+    g = load("world.npz")
+    ctx = mb.Context(tuple(int(v) for v in g["phase_space"]), a=cm.A, crf=cm.CRF)
+    ctx.build_world(seed=int(g["seed"]), t_set=float(g["t_set"]), ratio=(1, 0, 0))
+    got = cm.owned(ctx, ctx.download())
+    assert np.array_equal(got["id"], g["id"])
+    assert np.array_equal(got["type"], g["type"])
+    assert np.array_equal(got["x"], g["x"])
+    assert np.allclose(got["v"], g["v"], rtol=1e-11, atol=1e-13)  # reductions sum in a different order
+    assert abs(ctx.temperature()["T"] - float(g["temperature"])) < 1e-9
+    ctx.close()
