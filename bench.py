@@ -68,26 +68,63 @@ def peaks():
 # clocks: nvidia-smi sampled DURING the timed region
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in-process every 10 ms when pynvml is
+    importable (nvidia_ml_py), else `nvidia-smi -lms 50` as a child process. Started well before the timed region."""
     FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
               "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
               "clocks_event_reasons.sw_power_cap"]
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []       # (t, sm_mhz, sm_max_mhz, set(reasons))
         self.proc = None
+        self.stop = False
+        self.source = None
+        self.t0 = self.t1 = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + ",".join(self.FIELDS), "--format=csv,noheader,nounits",
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.th = threading.Thread(target=self._read_smi, daemon=True)
             self.th.start()
         except OSError:
             self.proc = None
-        self.t0 = self.t1 = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, self.mx, {n for b, n in self.NVML_REASONS if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            r = [c.strip() for c in line.split(",")]
+            if len(r) != len(self.FIELDS):
+                continue
+            try:
+                sm, mx = float(r[0]), float(r[1])
+            except ValueError:
+                continue
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((time.perf_counter(), sm, mx, {n for n, v in zip(names, r[3:]) if v.lower().startswith("active")}))
 
     def mark_start(self):
         self.t0 = time.perf_counter()
@@ -96,28 +133,26 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def finish(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06 and len(r) == len(self.FIELDS)]
-        if not rows:  # timed region shorter than one sample: take whatever was seen closest to it
-            rows = [r for _, r in self.rows[-3:] if len(r) == len(self.FIELDS)]
-        sm, mx, reasons = [], [], set()
-        for r in rows:
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)
+        self.stop = True
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= self.t1 + 0.02]
+        where = "timed region"
+        if not rows:  # timed region shorter than one sample: take whatever was seen closest to it
+            rows, where = self.rows[-3:], "nearest samples"
+        reasons = set()
+        for r in rows:
+            reasons |= r[3]
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source, "window": where}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -259,9 +294,14 @@ def run_b200(args):
             uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-    host, _ = synth.create_sub_box_state(phase, grid, coord, a=A, seed=466953, t_set=600.0, ratio=tuple(args.ratio), crf=CRF)
+    clocks = ClockSampler(local_rank)  # started early: it is sampling long before the timed region begins
+    # initial state built on the device by global atom id (misa_b200_build_world = WorldBuilder::build, seed 466953,
+    # 600 K): every sub-box cuts its part out of the same global state, no host init, no H2D
+    t_build = time.perf_counter()
+    ctx.build_world(seed=466953, t_set=600.0, ratio=tuple(args.ratio))
+    t_build = time.perf_counter() - t_build
+    host = np.zeros(ctx.n_ext, dtype=synth.ATOM_DTYPE)
     ctx.host_register(host)  # pinned: the e2e leg copies from / to this array every step
-    ctx.upload(host)
     ctx.prepare()
     atoms_per_gpu = ctx.n_owned
 
@@ -284,7 +324,6 @@ def run_b200(args):
     # which would flatter the timed region. The timed steps are those of the stationary NVE run BASELINE.json names.
     ctx.step(args.equil)
     ctx.step(max(args.warmup, 3))
-    clocks = ClockSampler(local_rank)
     barrier()
     l0 = ctx.launch_count()
     clocks.mark_start()
@@ -355,7 +394,7 @@ def run_b200(args):
         "roofline": roofline, "kernels": kernels, "step_hbm_gbs": step_gbs, "step_hbm_frac": step_gbs / peak,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "state": {"runaways_last_step": th["runaways"], "inter_atoms": th["n_inter"], "equil_steps": args.equil,
-                  "stencil_offsets": int(ctx.query("n_off")), "stencil_offsets_full": int(ctx.query("n_full")),
+                  "world_build_ms": 1e3 * t_build, "stencil_offsets": int(ctx.query("n_off")), "stencil_offsets_full": int(ctx.query("n_full")),
                   "max_displacement_A": ctx.query("dmax"), "temperature_K": th["mvv"] * 1.0364269e-4 / ((3 * th["n_atoms"] - 3) * 8.617343e-5)},
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:

@@ -107,3 +107,66 @@ def test_eight_gpus_track_oracle(tmp_path):
     w = _run(tmp_path, (12, 12, 12), (2, 2, 2), (90, 6, 4), steps=3)
     _compare(tmp_path, w, 1e-12, 1e-9)
     w.close()
+
+
+def _frontier_worker(rank, world, phase, grid, ratio, out_dir):
+    """SURVEY.md section 8f entry points on a decomposed box: device world build by global id, global temperature and
+    rescale (NCCL all-reduce), dump record stream per sub-box."""
+    lib = mb.load()
+    mb.capi._ck(lib.misa_b200_env_init(rank))
+    coord = (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
+    ctx = mb.Context(phase, grid=grid, coord=coord, a=cm.A, crf=cm.CRF)
+    ctx.make_offsets()
+    ctx.set_potential(*cm.host_potential())
+    uid_path = os.path.join(out_dir, "uid.bin")
+    if rank == 0:
+        with open(uid_path + ".tmp", "wb") as f:
+            f.write(ctx.comm_unique_id())
+        os.rename(uid_path + ".tmp", uid_path)
+    else:
+        t0 = time.time()
+        while not os.path.exists(uid_path):
+            assert time.time() - t0 < 60
+            time.sleep(0.01)
+    ctx.comm_init(open(uid_path, "rb").read(), rank, world)
+    ctx.build_world(seed=466953, t_set=600.0, ratio=ratio, alloy_seed=9)
+    t0 = ctx.temperature()
+    ctx.prepare()
+    ctx.step(4)
+    t1 = ctx.temperature()
+    ctx.rescale_to(350.0)
+    t2 = ctx.temperature()
+    np.save(os.path.join(out_dir, "lat%d.npy" % rank), ctx.download())
+    np.save(os.path.join(out_dir, "dump%d.npy" % rank), ctx.dump_records(4))
+    np.save(os.path.join(out_dir, "temps%d.npy" % rank), np.array([t0["T"], t1["T"], t2["T"], t0["n_atoms"]]))
+    ctx.close()
+
+
+def test_two_gpus_world_thermo_rescale_dump(tmp_path):
+    from misa_md_b200 import synth
+    phase, grid, ratio = (12, 8, 8), (2, 1, 1), (90, 6, 4)
+    if mb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_frontier_worker, args=(2, phase, grid, ratio, str(tmp_path)), nprocs=2, join=True)
+    st = synth.create_global_state(phase, a=cm.A, seed=466953, t_set=600.0, ratio=ratio, alloy_seed=9)
+    w = cm.oracle_world(st, grid=grid, threads=2)
+    w.prepare()
+    for _ in range(4):
+        w.step()
+    t1 = w.temperature()
+    w.L.ora_rescale(w.h, 350.0)
+    temps = [np.load(os.path.join(str(tmp_path), "temps%d.npy" % r)) for r in range(2)]
+    assert np.array_equal(temps[0], temps[1])                # every rank holds the same global numbers
+    assert abs(temps[0][0] - 600.0) < 1e-9 and temps[0][3] == 2 * 12 * 8 * 8
+    assert abs(temps[0][1] - t1) / t1 < 1e-10
+    assert abs(temps[0][2] - 350.0) < 1e-9
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), "lat%d.npy" % r)).reshape(w.shape(r))[w.owned_slices(r)]
+        ref = w.atoms(r).reshape(w.shape(r))[w.owned_slices(r)]
+        assert np.array_equal(got["id"], ref["id"]) and np.array_equal(got["type"], ref["type"])
+        assert cm.rel_err(got["x"], ref["x"]) < 1e-12
+        assert cm.rel_err(got["v"], ref["v"]) < 1e-9
+        rec, want = np.load(os.path.join(str(tmp_path), "dump%d.npy" % r)), w.dump(r, 4)
+        assert np.array_equal(rec["id"], want["id"]) and np.array_equal(rec["type"], want["type"])
+        assert cm.rel_err(rec["x"], want["x"]) < 1e-12 and cm.rel_err(rec["v"], want["v"]) < 1e-9
+    w.close()
