@@ -103,6 +103,12 @@ struct misa_b200_ctx {
     int opt_fast = 1;                     // third-generation kernels (eam_fast.cuh)
     long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant
     bool seen_offlattice = false;         // a run-away / inter atom was reported by any sub-box since the last census
+    int opt_dilute = 1;                   // dilute-alloy kernels (eam_dilute.cuh) when one species holds >= 90 % of the sites
+    // static minority-neighbour lists (eam_fast.cuh, built by prepare(); valid until atoms are replaced or anything runs away)
+    unsigned char *d_mcount = nullptr, *d_mentry = nullptr;
+    int *d_minor = nullptr, *d_minor_count = nullptr; // device indices of the owned minority-species atoms
+    int n_minor = 0, minor_maj = 0;
+    bool minor_valid = false;
     int opt_smem = 1;                     // use the shared-memory table kernels when possible
     double stage_r_lo = 2.0;              // tables are staged for r >= stage_r_lo (Angstrom)
     // halo

@@ -191,16 +191,62 @@ __device__ __forceinline__ double tex_f64(const cudaTextureObject_t t, const int
     return __hiloint2double(v.y, v.x);
 }
 
+// ---- dilute alloys (one species >= 90 % of the sites, e.g. Fe-Cu-Ni 97:2:1) ------------------------------------
+// The per-lane staged-or-global choice of the multi-species variants makes nearly every warp-level pair issue BOTH
+// paths (86 % of them contain a minority lane at 97:2:1): force 1.16 ms against 0.79 ms for pure Fe. A first attempt
+// that listed minority pairs from inside the loop cost more than it saved (+50 % warp instructions under the
+// 64-register cap, profiles/r01r_ncu_dilute_inloop_summary.txt). What works: species sit on fixed lattice sites as
+// long as nothing runs away, so the sites of minority NEIGHBOURS are a static per-atom list (built once in
+// prepare(): up to MINOR_CAP one-byte indices into the widest pruned offset list). The main loop is then the
+// SINGLE-species loop, untouched -- every pair evaluated from the staged majority tables -- and an epilogue replaces
+// the few listed pairs: + pair(true species) - pair(majority species), both from the global Hermite block.
+// Atoms whose OWN species is a minority one are skipped by the force kernel and done by k_force_minor, one warp each.
+#define MINOR_CAP 16
+#define MINOR_OVERFLOW 255
+struct MinorList {
+    const unsigned char *count;   // [n_ext] entries of site d, MINOR_OVERFLOW: more than MINOR_CAP (atom recomputed generically)
+    const unsigned char *entry;   // [MINOR_CAP][n_ext] bits 0-6: index into offs (n_offs <= 128); bit 7: which of the two minority species
+    const int *offs;              // [2][n_offs] the offset list the indices refer to (widest pruned level)
+    int n_offs;
+    long long n_ext;
+    int maj;
+};
+// the two species that are not `maj`, in ascending order: which = 0 / 1
+__host__ __device__ __forceinline__ int minor_species(const int maj, const int which) { return which ? (maj == 2 ? 1 : 2) : (maj == 0 ? 1 : 0); }
+// one pair from the GLOBAL Hermite block (any species), same arithmetic as the loops below
+__device__ __forceinline__ double generic_rho_pair(const double2 *__restrict__ herm, const size_t tstride, const int tj, const double d2,
+                                                   const double inv_dr, const int n_m1) {
+    const double r = d2 * rsqrt_fast(d2);
+    const Split sx = split_fast(r, inv_dr, n_m1, 1);
+    const double2 *row = herm + (size_t)tj * tstride + sx.m;
+    return hval(hbasis(sx.p), __ldg(row), __ldg(row + 1));
+}
+__device__ __forceinline__ double generic_force_pair(const double2 *__restrict__ herm, const size_t tstride, const int nt, const int ti, const int tj,
+                                                     const double d2, const double dfi, const double dfj, const double inv_dr, const int n_m1) {
+    const double recip = rsqrt_fast(d2);
+    const Split sx = split_fast(d2 * recip, inv_dr, n_m1, 1);
+    const HBasis hb = hbasis(sx.p);
+    const HSlope hs = hslope(sx.p);
+    const double2 *rp = herm + (size_t)(nt + ti * nt + tj) * tstride + sx.m;
+    const double2 *ri = herm + (size_t)ti * tstride + sx.m;
+    const double2 *rj = herm + (size_t)tj * tstride + sx.m;
+    const double2 p0 = __ldg(rp), p1 = __ldg(rp + 1);
+    const double z2 = hval(hb, p0, p1), z2p = hder(hs, p0, p1);
+    const double emb = hder(hs, __ldg(ri), __ldg(ri + 1)) * dfj + hder(hs, __ldg(rj), __ldg(rj + 1)) * dfi;
+    return -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
+}
+
 // ---- K1 rho (+ K2 df fused): atom::latRho / latDf (reference src/atom.cpp:151-192,286-309), full-list gather ----
 // SINGLE: every valid site has type sp.single; staged slot 0 = elec[single], slot 1 = phi[single][single].
 // NOVAC : the census found no vacant site (ghosts included) -> no per-neighbour type test.
 // ACCUM : add to the existing rho (compat hook semantics / inter-atom pass ran first) instead of overwriting.
 // The offset list is sorted by site separation; its first n_near entries (sites >= 0.1a inside the cutoff) are
 // evaluated without any branch (two independent pairs in flight per thread), the rest behind a warp vote.
-template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM>
+// DILUTE: SINGLE loop over the majority tables + the minority-neighbour epilogue (see above).
+template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM, bool DILUTE = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
-        const TexAll tex, const RegionList rl, const LevelSel ls) {
+        const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList()) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
     const int *offs = offs_h;
     int n_off = n_off_h, n_near = n_near_h;
@@ -263,9 +309,36 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
             if (__any_sync(0xffffffffu, in)) pair(d2, in, tj);
         }
-        const bool low = mmin < row_lo;
+        bool low = mmin < row_lo;
+        if (DILUTE) {
+            const int nm = ml.count[d];
+            low = low || nm == MINOR_OVERFLOW;
+            const int maxn = __reduce_max_sync(0xffffffffu, nm == MINOR_OVERFLOW ? 0 : nm);
+            const int *moff = ml.offs + (par ? ml.n_offs : 0);
+            // neighbour fields through the TEX pipe (the LSU pipe is the loaded one), the majority term that is taken
+            // back from the staged tables; rows below the staged range make the atom `low` (generic recompute) anyway
+EAM_UNROLL(2)
+            for (int k = 0; k < maxn; k++) {
+                if (k < nm && nm != MINOR_OVERFLOW) {
+                    const int e = ml.entry[(size_t)k * ml.n_ext + d];   // species are static while the lists are valid: no type gather
+                    const int j = d + moff[e & 127];
+                    const int tj = minor_species(ml.maj, e >> 7);
+                    const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+                    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    if (d2 < rc2) {
+                        const double r = d2 * rsqrt_fast(d2);
+                        const Split sx = split_fast(r, inv_dr, n_m1, row_lo);
+                        const HBasis hb = hbasis(sx.p);
+                        double2 r0, r1;
+                        rows_s(b_el0, sx.m, r0, r1);
+                        const double2 *row = g_herm + (size_t)tj * tstride + sx.m;
+                        acc += hval(hb, __ldg(row), __ldg(row + 1)) - hval(hb, r0, r1);
+                    }
+                }
+            }
+        }
         if (__any_sync(0xffffffffu, low)) {
-            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], NEEDTYPE ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d);
+            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d);
         }
         if (!live) continue;
         if (ti < 0) {
@@ -282,10 +355,10 @@ EAM_UNROLL(EAM_UNROLL_FAR)
 // eam::toForce (oracle/pot.c:pot_to_force): phi = z2/r, phi' = z2'/r - phi/r, fpair = -(phi' + emb)/r with
 // emb = rho'_i(r) df_j + rho'_j(r) df_i; z2' and rho' are slopes per knot times 1/dr, factored out:
 //   fpair = -(1/r) * ( (1/dr) * (z2'_p / r + emb_p) - z2 / r^2 )
-template <bool SINGLE, bool NOVAC, bool ACCUM>
+template <bool SINGLE, bool NOVAC, bool ACCUM, bool DILUTE = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
-          const TexAll tex, const RegionList rl, const LevelSel ls) {
+          const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList()) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
     const int *offs = offs_h;
     int n_off = n_off_h, n_near = n_near_h;
@@ -391,20 +464,133 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
             if (__any_sync(0xffffffffu, in)) pair(dx, dy, dz, d2, in, tj, j);
         }
-        const bool low = mmin < row_lo;
+        bool low = mmin < row_lo;
+        if (DILUTE) {
+            const bool mine = ti == ml.maj;       // minority central atoms: k_force_minor writes them
+            const int nm = mine ? (int)ml.count[d] : 0;
+            low = mine && (low || nm == MINOR_OVERFLOW);
+            const int maxn = __reduce_max_sync(0xffffffffu, nm == MINOR_OVERFLOW ? 0 : nm);
+            const int *moff = ml.offs + (par ? ml.n_offs : 0);
+EAM_UNROLL(2)
+            for (int k = 0; k < maxn; k++) {
+                if (k < nm && nm != MINOR_OVERFLOW) {
+                    const int e = ml.entry[(size_t)k * ml.n_ext + d];   // species are static while the lists are valid: no type gather
+                    const int j = d + moff[e & 127];
+                    const int tj = minor_species(ml.maj, e >> 7);
+                    const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+                    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    if (d2 < rc2) {
+                        const double dfj = tex_f64(tx, j + 3 * ns);
+                        const double recip = rsqrt_fast(d2);
+                        const Split sx = split_fast(d2 * recip, inv_dr, n_m1, row_lo);
+                        const HBasis hb = hbasis(sx.p);
+                        const HSlope hs = hslope(sx.p);
+                        double2 r0, r1;
+                        // majority term as the loop evaluated it (staged rows), to be taken back
+                        rows_s(b_ph0, sx.m, r0, r1);
+                        const double z2m = hval(hb, r0, r1), z2pm = hder(hs, r0, r1);
+                        rows_s(b_el0, sx.m, r0, r1);
+                        const double rho_p_maj = hder(hs, r0, r1);
+                        const double fpm = -recip * fma(inv_dr, fma(z2pm, recip, rho_p_maj * (dfi + dfj)), -(z2m * (recip * recip)));
+                        // the pair as it is: phi[maj][tj], rho'_maj * df_j + rho'_tj * df_i
+                        const double2 *rp = g_herm + (size_t)(nt + ml.maj * nt + tj) * tstride + sx.m;
+                        const double2 *rj = g_herm + (size_t)tj * tstride + sx.m;
+                        const double2 p0 = __ldg(rp), p1 = __ldg(rp + 1);
+                        const double z2 = hval(hb, p0, p1), z2p = hder(hs, p0, p1);
+                        const double emb = fma(rho_p_maj, dfj, hder(hs, __ldg(rj), __ldg(rj + 1)) * dfi);
+                        const double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip))) - fpm;
+                        fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
+                    }
+                }
+            }
+        }
         if (__any_sync(0xffffffffu, low)) {
             if (low) {
-                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, NEEDTYPE ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types,
+                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types,
                                                   tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d, tic);
                 fx = f.x; fy = f.y; fz = f.z;
             }
         }
         if (!live) continue;
+        if (DILUTE && ti >= 0 && ti != ml.maj) continue;
         if (ti < 0) {
             if (!ACCUM) { s.f[0][d] = 0.0; s.f[1][d] = 0.0; s.f[2][d] = 0.0; }
             continue;
         }
         if (ACCUM) { fx += s.f[0][d]; fy += s.f[1][d]; fz += s.f[2][d]; }
         s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz;
+    }
+}
+
+// ---- dilute alloys: the static lists (built in prepare(), after the first ghost exchange) and the minority atoms ----
+// per owned site: which entries of the widest pruned offset list point at a site holding a minority atom
+__global__ void __launch_bounds__(MISA_BLOCK) k_build_minor_lists(const Geo g, const int8_t *__restrict__ type, const int maj, const int blocks_per_parity,
+                                                                  const int *__restrict__ offs, const int n_offs, unsigned char *__restrict__ count,
+                                                                  unsigned char *__restrict__ entry, int *__restrict__ minor, int *__restrict__ n_minor) {
+    const int p = blockIdx.x >= blocks_per_parity;
+    const long long c = (long long)(blockIdx.x - p * blocks_per_parity) * MISA_BLOCK + threadIdx.x;
+    int d = -1, t = -1;
+    if (c < g.n_cells_owned) {
+        int cx, y, z;
+        d = owned_cell_to_dev(g, p, c, cx, y, z);
+        t = type[d];
+        const int *off = offs + (p ? n_offs : 0);
+        int cnt = 0;
+        for (int q = 0; q < n_offs; q++) {
+            const int tj = type[d + off[q]];
+            if (tj >= 0 && tj != maj) {
+                if (cnt < MINOR_CAP) entry[(size_t)cnt * g.n_ext + d] = (unsigned char)(q | (tj == minor_species(maj, 1) ? 128 : 0));
+                cnt++;
+            }
+        }
+        count[d] = (unsigned char)(cnt > MINOR_CAP ? MINOR_OVERFLOW : cnt);
+    }
+    // owned atoms of a minority species -> device index list (order irrelevant: entries are independent)
+    const bool minor_atom = d >= 0 && t >= 0 && t != maj;
+    const unsigned m = __ballot_sync(0xffffffffu, minor_atom);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(n_minor, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (minor_atom) minor[base + __popc(m & ((1u << lane) - 1u))] = d;
+}
+// force on the minority atoms, one warp each: lanes stride the offsets of the atom's parity, fixed-shape butterfly
+// reduction (deterministic per atom; atoms are independent of each other)
+__global__ void __launch_bounds__(256) k_force_minor(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h,
+                                                     const int n_off_h, const LevelSel ls, const int *__restrict__ list, const int n, const TexAll tex) {
+    const int *offs = offs_h;
+    int n_off = n_off_h, n_near = 0;
+    select_list(ls, offs, n_off, n_near);
+    const int lane = threadIdx.x & 31;
+    const int nt = tb.n_types, n_m1 = tb.n_r - 1;
+    const double2 *__restrict__ g_herm = sp.g_elec[0];
+    const size_t tstride = (size_t)tb.n_r + 1;
+    const double rc2 = g.rc2, inv_dr = tb.inv_dr;
+    for (int w = (blockIdx.x * 256 + threadIdx.x) >> 5; w < n; w += (gridDim.x * 256) >> 5) {
+        const int d = list[w];
+        const int ti = s.type[d];
+        if (ti < 0) continue;                 // cannot happen while the lists are valid (no run-away since they were built)
+        const int *off = offs + (d >= g.H ? n_off : 0);
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        // every lane gathers a different neighbour: scattered 8-byte loads, on the TEX pipe (idle here) rather than LSU
+EAM_UNROLL(2)
+        for (int q = lane; q < n_off; q += 32) {
+            const int j = d + off[q];
+            const int tj = s.type[j];
+            const double dx = xi - tex_f64(tex.t, j), dy = yi - tex_f64(tex.t, j + tex.ns), dz = zi - tex_f64(tex.t, j + 2 * tex.ns);
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (tj >= 0 && d2 < rc2) {
+                const double fp = generic_force_pair(g_herm, tstride, nt, ti, tj, d2, dfi, tex_f64(tex.t, j + 3 * tex.ns), inv_dr, n_m1);
+                fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (lane == 0) { s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz; }
     }
 }

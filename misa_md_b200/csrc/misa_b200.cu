@@ -91,6 +91,7 @@ static int census_fetch(misa_b200_ctx *c);
 static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off, int *n_near = nullptr);
 static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes);
 static inline bool no_vacancy(const misa_b200_ctx *c);
+static bool dilute_ok(const misa_b200_ctx *c, const StagePlan &sp, bool accum);
 static int smem_kernels_init(int optin) {
     static bool done = false;
     if (done) return 0;
@@ -108,6 +109,9 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_force_f<true, true, false>)); OPTIN((k_force_f<true, true, true>));
     OPTIN((k_force_f<true, false, false>)); OPTIN((k_force_f<true, false, true>));
     OPTIN((k_force_f<false, false, false>)); OPTIN((k_force_f<false, false, true>));
+    OPTIN((k_rho_f<true, true, true, false, true>)); OPTIN((k_rho_f<true, true, false, false, true>));
+    OPTIN((k_rho_f<true, false, true, false, true>)); OPTIN((k_rho_f<true, false, false, false, true>));
+    OPTIN((k_force_f<true, true, false, true>)); OPTIN((k_force_f<true, false, false, true>));
 #undef OPTIN
     done = true;
     return 0;
@@ -314,6 +318,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
+    cudaFree(c->d_minor); cudaFree(c->d_minor_count); cudaFree(c->d_mcount); cudaFree(c->d_mentry);
     cudaFree(c->d_dump); cudaFree(c->d_dump_base); cudaFree(c->d_dump_total); cudaFree(c->d_dump_count); cudaFreeHost(c->h_dump_total);
     inter_free(c);
     for (int k = 0; k < MISA_B200_K_COUNT; k++) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
@@ -562,6 +567,7 @@ static int ensure_aos(misa_b200_ctx *c) {
 }
 static int h2d_aos(misa_b200_ctx *c, const void *atoms, int fields) {
     TRY(ensure_aos(c));
+    c->minor_valid = false; // the host may have put any species anywhere
     CU(cudaMemcpyAsync(c->d_aos, atoms, (size_t)c->geo.n_ext * 104, cudaMemcpyHostToDevice, c->stream));
     Slot sl(c, MISA_B200_K_XFER);
     k_aos_to_soa<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->geo.H, (const unsigned long long *)c->d_aos, c->s, fields);
@@ -638,6 +644,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "tex")) c->opt_tex = value;
     else if (!strcmp(name, "novac")) c->opt_novac = value;
     else if (!strcmp(name, "fast")) c->opt_fast = value;
+    else if (!strcmp(name, "dilute")) c->opt_dilute = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
     else if (!strcmp(name, "overlap")) c->opt_overlap = value;
@@ -663,6 +670,8 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
     else if (!strcmp(name, "single")) *value = planned ? sp.single : -2;
     else if (!strcmp(name, "novac")) *value = no_vacancy(c) ? 1 : 0;
     else if (!strcmp(name, "smem_bytes")) *value = planned ? (double)sb : 0.0;
+    else if (!strcmp(name, "dilute")) *value = planned && dilute_ok(c, sp, false) ? 1 : 0;
+    else if (!strcmp(name, "n_minor")) *value = c->minor_valid ? c->n_minor : -1;
     else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
     return 0;
 }
@@ -863,6 +872,51 @@ static inline bool no_vacancy(const misa_b200_ctx *c) {
     return c->opt_novac && c->n_valid_sites == c->geo.n_ext && !c->seen_offlattice;
 }
 
+// Dilute alloy (one species holds >= 90 % of the valid sites): the SINGLE-species loop over the majority tables plus
+// the minority-neighbour epilogue (eam_fast.cuh). Needs the static lists of prepare(), nothing off-lattice since, and
+// every atom within 0.2a of its site (the lists cover the widest pruned stencil).
+static bool dilute_ok(const misa_b200_ctx *c, const StagePlan &sp, bool accum) {
+    if (!c->opt_dilute || !c->opt_prune || accum || sp.single >= 0 || !c->minor_valid || c->minor_maj != sp.staged_id[0]) return false;
+    if (c->seen_offlattice || c->inter_active || has_inter(c)) return false;
+    return c->dmax_valid && sqrt(c->dmax2) + 1e-6 < 0.2 * c->geo.a;
+}
+static MinorList minor_list(const misa_b200_ctx *c) {
+    const int L = misa_b200_ctx::kLevels - 1;
+    MinorList ml;
+    ml.count = c->d_mcount; ml.entry = c->d_mentry;
+    ml.offs = c->d_off_levels + c->level_ofs[L]; ml.n_offs = c->level_n[L];
+    ml.n_ext = c->geo.n_ext; ml.maj = c->minor_maj;
+    return ml;
+}
+static int build_minor_lists(misa_b200_ctx *c) {
+    c->minor_valid = false;
+    StagePlan sp;
+    size_t sb;
+    const int L = misa_b200_ctx::kLevels - 1;
+    if (!c->opt_dilute || !c->have_pot || !make_plan(c, sp, sb) || sp.single >= 0 || c->level_n[L] <= 0 || c->level_n[L] > 128) return 0;
+    unsigned long long total = 0;
+    for (int t = 0; t < MISA_MAX_TYPES; t++) total += c->census[t];
+    if (total == 0 || (double)c->census[sp.staged_id[0]] < 0.9 * (double)total) return 0;
+    const Geo &g = c->geo;
+    if (!c->d_mcount) {
+        TRY(dmalloc(&c->d_mcount, (size_t)g.n_ext));
+        TRY(dmalloc(&c->d_mentry, (size_t)g.n_ext * MINOR_CAP));
+        TRY(dmalloc(&c->d_minor, (size_t)2 * g.n_cells_owned));
+        TRY(dmalloc(&c->d_minor_count, 1));
+    }
+    const int bpp = nblk(g.n_cells_owned);
+    CU(cudaMemsetAsync(c->d_minor_count, 0, sizeof(int), c->stream));
+    k_build_minor_lists<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s.type, sp.staged_id[0], bpp, c->d_off_levels + c->level_ofs[L], c->level_n[L],
+                                                              c->d_mcount, c->d_mentry, c->d_minor, c->d_minor_count);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&c->n_minor, c->d_minor_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->minor_maj = sp.staged_id[0];
+    c->minor_valid = true;
+    return 0;
+}
+
 // whole sub-box / interior (no ghost site within the stencil reach) / the six boundary slabs around it
 static RegionList make_regions(const Geo &g, int which) {
     RegionList rl;
@@ -917,7 +971,17 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const RegionList rl = make_regions(g, so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;
-#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls)
+        if (dilute_ok(c, sp, accum)) {
+            const MinorList ml = minor_list(c);
+#define RHO_D(N, F) k_rho_f<true, N, F, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, ml)
+            if (novac) { if (fuse_df) RHO_D(true, true); else RHO_D(true, false); }
+            else { if (fuse_df) RHO_D(false, true); else RHO_D(false, false); }
+#undef RHO_D
+            c->launches++;
+            CU(cudaGetLastError());
+            return 0;
+        }
+#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, MinorList())
 #define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
         if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
 #undef RHO_FA
@@ -976,8 +1040,30 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     Slot sl(c, MISA_B200_K_FORCE);
     StagePlan sp;
     size_t sb;
-    // alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the second
-    // generation's staged/divergent one (1.50 vs 1.18 ms at 97:2:1), so multi-species force stays on k_force_s
+    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
+        const int grid = std::max(1, c->sm_count - so.reserve_sms);
+        const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+        const RegionList rl = make_regions(g, so.region);
+        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const MinorList ml = minor_list(c);
+        if (rl.units > 0) {
+            if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, ml);
+            else k_force_f<true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, ml);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        // atoms of a minority species: ALL of them with the launch that runs after the df halo has arrived (the whole-box
+        // launch or the boundary one), one warp per atom
+        if (so.region != 1 && c->n_minor > 0) {
+            const int mgrid = std::min((c->n_minor + 7) / 8, std::max(1, c->sm_count) * 8);
+            k_force_minor<<<mgrid, 256, 0, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, ls, c->d_minor, c->n_minor, tex);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        return 0;
+    }
+    // non-dilute alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the
+    // second generation's staged/divergent one (1.50 vs 1.18 ms at 97:2:1), so multi-species force stays on k_force_s
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
@@ -985,8 +1071,8 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const RegionList rl = make_regions(g, so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;
-#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls); \
-                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls); } while (0)
+#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, MinorList()); \
+                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, MinorList()); } while (0)
         if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
 #undef FORCE_F
         c->launches++;
@@ -1157,6 +1243,7 @@ extern "C" int misa_b200_prepare(misa_b200_ctx *c) {
     TRY(census_fetch(c));
     c->census_boxes = 1;
     TRY(measure_displacement(c));
+    TRY(build_minor_lists(c));     // dilute alloys: species sit on fixed sites until something runs away
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
     TRY(update_activity(c));
     if (c->inter_active) { TRY(inter_exchange(c)); TRY(inter_border(c)); }
@@ -1476,6 +1563,7 @@ extern "C" int misa_b200_build_world(misa_b200_ctx *c, uint32_t seed, double t_s
     TRY(census_fetch(c));
     c->have_atoms = true;
     c->dmax_valid = false;
+    c->minor_valid = false;
     return 0;
 }
 

@@ -275,3 +275,53 @@ def test_compat_hooks_match_cpu_branch():
     assert np.array_equal(host["x"], ref["x"]) and np.array_equal(host["id"], ref["id"])
     ctx.close()
     w.close()
+
+
+@pytest.mark.parametrize("ratio,vac", [((97, 2, 1), 0), ((92, 5, 3), 7), ((3, 95, 2), 0)])
+def test_dilute_alloy_kernels_match_oracle(ratio, vac):
+    """eam_dilute.cuh (majority tables branch-free, minority pairs listed and corrected, minority atoms one warp
+    each) against the oracle and against the general multi-species kernels, over a few steps."""
+    st = cm.make_state((10, 9, 11), ratio=ratio, sigma=0.06, vacancies=vac)
+    w = cm.oracle_world(st)
+    w.prepare()
+    out = {}
+    for dilute in (1, 0):
+        ctx = cm.gpu_context(st)
+        ctx.set_option("dilute", dilute)
+        ctx.prepare()
+        assert ctx.query("dilute") == dilute
+        first = cm.owned(ctx, ctx.download()).copy()
+        ref = cm.owned(ctx, w.atoms(0))
+        valid = ref["type"] >= 0
+        for fld in ("rho", "df", "f"):
+            assert cm.rel_err(first[fld][valid], ref[fld][valid]) < TOL, (dilute, fld)
+        ctx.step(3)
+        out[dilute] = cm.owned(ctx, ctx.download()).copy()
+        ctx.close()
+    for _ in range(3):
+        w.step()
+    ref = cm.owned(ctx, w.atoms(0))
+    valid = ref["type"] >= 0
+    for dilute in (1, 0):
+        assert np.array_equal(out[dilute]["type"], ref["type"])
+        assert cm.rel_err(out[dilute]["rho"][valid], ref["rho"][valid]) < TOL
+        assert cm.rel_err(out[dilute]["f"][valid], ref["f"][valid]) < 1e-9
+    assert cm.rel_err(out[1]["x"][valid], out[0]["x"][valid]) < 1e-13
+    w.close()
+
+
+def test_dilute_alloy_solute_cluster_overflows_the_pair_list():
+    """A compact Cu precipitate: atoms next to it have more than EAM_LIST_CAP minority neighbours, so the per-lane
+    list overflows and the atom is recomputed by the generic routine; Cu atoms inside it go through k_force_minor."""
+    st = cm.make_state((12, 12, 12), ratio=(1, 0, 0), sigma=0.05)
+    st["type"][4:8, 4:8, 8:16] = 1      # 4x4x4 cells of Cu = 128 atoms of 3456 (3.7 %)
+    w = cm.oracle_world(st)
+    w.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    assert ctx.query("dilute") == 1
+    got, ref = cm.owned(ctx, ctx.download()), cm.owned(ctx, w.atoms(0))
+    for fld in ("rho", "df", "f"):
+        assert cm.rel_err(got[fld], ref[fld]) < TOL, fld
+    ctx.close()
+    w.close()
