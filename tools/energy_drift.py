@@ -10,12 +10,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 ratio = tuple(int(v) for v in sys.argv[3:6]) if len(sys.argv) > 5 else (1, 0, 0)
 P = (n, n, n)
-st = synth.create_global_state(P, ratio=ratio)
 ctx = mb.Context(P)
 ctx.make_offsets()
 ctx.set_potential(*mb.capi.potential_in_type_order(mb.capi.read_setfl(mb.SETFL_PATH)))
-arr, _ = synth.scatter_to_sub_box(st, (1, 1, 1), (0, 0, 0))
-ctx.upload(arr)
+ctx.build_world(seed=466953, t_set=600.0, ratio=ratio)   # WorldBuilder on the device, by global atom id
 ctx.prepare()
 
 
