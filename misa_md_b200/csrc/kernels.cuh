@@ -189,7 +189,10 @@ __device__ __forceinline__ void report_max(double v, unsigned long long *__restr
         if (bits > *reinterpret_cast<volatile unsigned long long *>(out)) atomicMax(out, bits);
     }
 }
-// squared displacement of the atom from its ideal site after the drift (0 for vacant sites)
+// squared displacement of the atom from its ideal site after the drift (0 for vacant sites).
+// KICK2: the second half-kick of the step that just finished (NewtonMotion::secondstep, same f) is applied first --
+// inside a multi-step call the two streaming passes over v and f become one (bit-identical: the same two rounded adds)
+template <bool KICK2>
 __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const VerletPar &vp, const int p, const long long c,
                                                int *__restrict__ counters, int *__restrict__ runaway_sites, const int runaway_cap) {
     int cx, y, z;
@@ -201,7 +204,10 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
     double x[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const double v = __dadd_rn(s.v[k][d], __dmul_rn(cm, s.f[k][d]));
+        const double kick = __dmul_rn(cm, s.f[k][d]);
+        double v = s.v[k][d];
+        if (KICK2) v = __dadd_rn(v, kick);
+        v = __dadd_rn(v, kick);
         s.v[k][d] = v;
         x[k] = __dadd_rn(s.x[k][d], __dmul_rn(vp.dt, v));
         s.x[k][d] = x[k];
@@ -224,6 +230,7 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
 }
 
 
+template <bool KICK2>
 __global__ void __launch_bounds__(MISA_BLOCK)
 k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
           int *__restrict__ runaway_sites, const int runaway_cap, unsigned long long *__restrict__ stepinfo) {
@@ -231,7 +238,7 @@ k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
     const int b = blockIdx.x - p * blocks_per_parity;
     const long long c = (long long)b * blockDim.x + threadIdx.x;
     double dist = 0.0;
-    if (c < g.n_cells_owned) dist = verlet1_site(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
+    if (c < g.n_cells_owned) dist = verlet1_site<KICK2>(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
     report_max(dist, &stepinfo[1]);
 }
 // ---- K5 verlet-2: NewtonMotion::secondstep (reference src/newton_motion.cpp:57-74) -------------------

@@ -645,6 +645,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "novac")) c->opt_novac = value;
     else if (!strcmp(name, "fast")) c->opt_fast = value;
     else if (!strcmp(name, "dilute")) c->opt_dilute = value;
+    else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
     else if (!strcmp(name, "overlap")) c->opt_overlap = value;
@@ -1159,14 +1160,15 @@ static int update_activity(misa_b200_ctx *c) {
 }
 
 // NewtonMotion::firststep + the displacement test of atom::decide, enqueued on the main stream
-static int verlet1_enqueue(misa_b200_ctx *c) {
+static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     const VerletPar vp = verlet_par(c);
     Slot sl(c, MISA_B200_K_VERLET1);
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
     CU(cudaMemsetAsync(c->d_stepinfo, 0, 2 * sizeof(unsigned long long), c->stream));
-    k_verlet1<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
+    if (kick2) k_verlet1<true><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
+    else k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -1267,8 +1269,11 @@ static bool pipe_ok(const misa_b200_ctx *c) {
     return c->opt_pipe && c->opt_fast && c->opt_prune && c->opt_fuse && c->tex_all && !c->prof_on && !has_inter(c) && !c->inter_active &&
            c->stream2 && make_plan(c, sp, sb);
 }
-static int step_pipelined(misa_b200_ctx *c, bool &redone) {
+// kick2_in: the previous step of this call left its second half-kick to this step's k_verlet1<true>;
+// defer_out: the caller runs another step right after this one, so this step may do the same (*deferred says it did).
+static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false, bool defer_out = false, bool *deferred = nullptr) {
     redone = false;
+    if (deferred) *deferred = false;
     // The interior/boundary split pays when the exchange is long against what it costs (8 SMs left to the exchange
     // kernels + two extra launches): measured on B200, 100^3 cells per GPU -- 2x1x1 grid (one NCCL stage, 0.11 ms of
     // exchange): 1.50 ms in line vs 1.59 ms split; 2x2x2 grid (three stages, 0.38 ms): 1.81 ms in line vs 1.61 ms
@@ -1277,7 +1282,7 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone) {
     int nccl_dims = 0;
     for (int d = 0; d < 3; d++) nccl_dims += c->dom.grid_size[d] > 1;
     const bool overlap = c->opt_overlap > 1 || (c->opt_overlap == 1 && nccl_dims >= 1) || (c->opt_overlap < 0 && nccl_dims >= 2);
-    TRY(verlet1_enqueue(c));
+    TRY(verlet1_enqueue(c, kick2_in));
     StencilOpt whole, interior, boundary;
     whole.dmax2 = c->d_stepinfo_g + 1;
     interior.region = 1; interior.dmax2 = c->d_stepinfo + 1; interior.reserve_sms = c->opt_reserve;
@@ -1325,18 +1330,24 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone) {
         TRY(compute_eam(c));
     } else {
         TRY(verlet1_finish(c));
+        if (defer_out && c->opt_fuse_verlet && pipe_ok(c)) {   // the next k_verlet1 applies this step's second half-kick too
+            if (deferred) *deferred = true;
+            return 0;
+        }
     }
     return misa_b200_pass_verlet2(c);
 }
 
 extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
     TRY(ready(c));
+    bool pending_kick2 = false;   // never crosses the end of this call: the state a caller sees is a full step's
     for (int s = 0; s < n_steps; s++) {
         if (pipe_ok(c)) {
             bool redone;
-            TRY(step_pipelined(c, redone));
+            TRY(step_pipelined(c, redone, pending_kick2, s + 1 < n_steps, &pending_kick2));
             continue;
         }
+        if (pending_kick2) { TRY(misa_b200_pass_verlet2(c)); pending_kick2 = false; }
         TRY(misa_b200_pass_verlet1(c));
         TRY(misa_b200_pass_halo_x(c));
         if (!c->dmax_valid) TRY(measure_displacement(c));
@@ -1345,6 +1356,7 @@ extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
         TRY(compute_eam(c));
         TRY(misa_b200_pass_verlet2(c));
     }
+    if (pending_kick2) TRY(misa_b200_pass_verlet2(c));
     return 0;
 }
 

@@ -325,3 +325,26 @@ def test_dilute_alloy_solute_cluster_overflows_the_pair_list():
         assert cm.rel_err(got[fld], ref[fld]) < TOL, fld
     ctx.close()
     w.close()
+
+
+def test_fused_half_kicks_are_bit_identical():
+    """Inside one multi-step call the second half-kick of step k runs inside k_verlet1 of step k+1 (one pass over v
+    and f instead of two). Same two rounded adds: identical bits to stepping one call at a time, and to the option off."""
+    st = cm.make_state((10, 10, 10), ratio=(97, 2, 1), sigma=0.04)
+    out = []
+    for mode in ("one_call", "single_steps", "option_off"):
+        ctx = cm.gpu_context(st)
+        if mode == "option_off":
+            ctx.set_option("fuse_verlet", 0)
+        ctx.prepare()
+        if mode == "single_steps":
+            for _ in range(6):
+                ctx.step(1)
+        else:
+            ctx.step(6)
+        assert ctx.query("pipe_steps") == 6
+        out.append(cm.owned(ctx, ctx.download()).copy())
+        ctx.close()
+    for other in out[1:]:
+        for fld in ("x", "v", "f", "rho", "df"):
+            assert np.array_equal(out[0][fld], other[fld]), fld
