@@ -43,6 +43,7 @@ struct Soa {
     double *rho, *df;
     int8_t *type;
     unsigned long long *id;
+    unsigned char *ulev;   // ceil(|x - site| / 0.01a) of the valid atom on the site (k_verlet1 / k_max_displacement): per-warp stencil pruning
 };
 
 struct InterSoa {  // off-lattice atoms: [0, n_local) local, [cap/2, cap/2 + n_ghost) ghost copies
@@ -75,6 +76,8 @@ struct misa_b200_ctx {
     // pruned stencils by displacement level L: every valid atom within L*0.01a of its site => two lattice atoms
     // can only be within r_c if their SITES are closer than (crf + 0.02 L) a. L = 20 is atom::decide's own bound.
     static const int kLevels = 21;
+    static const int kPairLevels = 41;    // prefix lengths of the distance-sorted full list: sites closer than (crf + 0.01 L) a
+    int prefix_n[kPairLevels] = {0};
     int level_n[kLevels] = {0};
     int level_near[kLevels] = {0};        // leading entries (lists are sorted by site distance) that are almost surely in range
     int near_full = 0;
@@ -111,6 +114,14 @@ struct misa_b200_ctx {
     int n_minor = 0, minor_maj = 0;
     bool minor_valid = false;
     int opt_smem = 1;                     // use the shared-memory table kernels when possible
+    // pair-symmetric stencil passes (eam_sym.cuh): the leading n_half entries of every offset list are the "upper"
+    // (reference half-list, src/atom/neighbour_index.inl:79-92) near offsets; their per-pair scalars go through d_pair
+    int opt_sym = 0;                      // OFF by default: measured slower than the full-list kernels
+    int n_half = 0;                       // 0: lists not symmetric-capable
+    int sym_lo[3] = {0, 0, 0}, sym_hi[3] = {0, 0, 0}; // cells below / above the owned box whose sites own a pair with an owned atom
+    int2 *d_lo_tab = nullptr;             // [2][n_half] per central parity: (device offset to the lower neighbour, its slot)
+    double *d_pair = nullptr;             // [n_half][n_ext]
+    size_t pair_elems = 0;
     double stage_r_lo = 2.0;              // tables are staged for r >= stage_r_lo (Angstrom)
     // halo
     HaloList halo[3][2];

@@ -248,13 +248,13 @@ __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
         const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList()) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
-    const int *offs = offs_h;
-    int n_off = n_off_h, n_near = n_near_h;
-    select_list(ls, offs, n_off, n_near);
+    const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
+    const int n_list = n_off_h, n_near = n_near_h;
+    const int lg = base_level(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
-    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list);
     if (!SINGLE && EAM_MULTI_GENERIC) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
@@ -274,7 +274,8 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
         const int ti = s.type[d];
-        const int *off = s_off + (par ? n_off : 0);
+        const int *off = s_off + (par ? n_list : 0);
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double acc = 0.0;
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
@@ -338,7 +339,7 @@ EAM_UNROLL(2)
             }
         }
         if (__any_sync(0xffffffffu, low)) {
-            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d);
+            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d);
         }
         if (!live) continue;
         if (ti < 0) {
@@ -360,13 +361,13 @@ __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
           const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList()) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
-    const int *offs = offs_h;
-    int n_off = n_off_h, n_near = n_near_h;
-    select_list(ls, offs, n_off, n_near);
+    const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
+    const int n_list = n_off_h, n_near = n_near_h;
+    const int lg = base_level(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
-    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list);
     if (!SINGLE && EAM_MULTI_GENERIC) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
@@ -388,7 +389,8 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);
         const int ti = s.type[d];
         const int tic = max(ti, 0);
-        const int *off = s_off + (par ? n_off : 0);
+        const int *off = s_off + (par ? n_list : 0);
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         unsigned long long d_eli = 0;
         if (!SINGLE && EAM_MULTI_GENERIC) d_eli = dir[tic];
@@ -507,7 +509,7 @@ EAM_UNROLL(2)
         if (__any_sync(0xffffffffu, low)) {
             if (low) {
                 const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types,
-                                                  tb.n_r, inv_dr, rc2, offs + (par ? n_off : 0), n_off, d, tic);
+                                                  tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d, tic);
                 fx = f.x; fy = f.y; fz = f.z;
             }
         }

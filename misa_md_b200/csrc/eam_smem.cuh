@@ -175,12 +175,19 @@ __device__ __forceinline__ int region_unit_to_dev(const Geo &g, const RegionList
 // ---- device-side choice of the pruned offset list from the largest displacement measured by k_verlet1 in the
 //      SAME step (no host round trip between the integrator and the stencil kernels; host twin: pick_list) ------
 #define EAM_LEVELS 21
+#define EAM_PAIR_LEVELS 41
 struct LevelSel {
-    const unsigned long long *dmax2_bits;   // null: use the list the host passed
+    const unsigned long long *dmax2_bits;   // null: use the list the host passed (second-generation kernels) / host_level
     const int *levels, *full;               // d_off_levels, d_off_full
     int n[EAM_LEVELS], near_[EAM_LEVELS], ofs[EAM_LEVELS];
     int n_full, near_full;
     double step;                            // 0.01 a
+    // third / fourth generation (eam_fast.cuh, eam_sym.cuh): the full list is sorted by site separation behind the near
+    // group, so every pruned list is a PREFIX of it, chosen per warp from the displacement levels of its own 32 atoms
+    // plus the global maximum (the partner's bound): sites closer than (crf + 0.01 (lw + lg)) a
+    const unsigned char *ulev;
+    int prefix[EAM_PAIR_LEVELS];
+    int host_level;                         // lg when dmax2_bits is null; -1: no pruning (full list)
 };
 __device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs, int &n_off, int &n_near) {
     if (!ls.dmax2_bits) return;
@@ -188,6 +195,17 @@ __device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs
     const int L = (int)ceil(d / ls.step);
     if (L < EAM_LEVELS && ls.n[min(L, EAM_LEVELS - 1)] > 0) { offs = ls.levels + ls.ofs[L]; n_off = ls.n[L]; n_near = ls.near_[L]; }
     else { offs = ls.full; n_off = ls.n_full; n_near = ls.near_full; }
+}
+// global displacement level (the bound on the partner atom of any pair)
+__device__ __forceinline__ int base_level(const LevelSel &ls) {
+    if (!ls.dmax2_bits) return ls.host_level;
+    const double d = sqrt(__longlong_as_double((long long)*ls.dmax2_bits)) + 1e-6;
+    return (int)min(ceil(d / ls.step), 1000.0);
+}
+// offsets a warp loops: lw = largest displacement level among its own atoms (warp-uniform)
+__device__ __forceinline__ int list_len(const LevelSel &ls, const int lg, const int lw) {
+    const int L = lg + lw;
+    return (lg >= 0 && L < EAM_PAIR_LEVELS) ? ls.prefix[L] : ls.n_full;
 }
 
 // ---- neighbour field access: plain global loads (LSU pipe) or texture fetches (TEX pipe of the same L1) -----

@@ -189,6 +189,11 @@ __device__ __forceinline__ void report_max(double v, unsigned long long *__restr
         if (bits > *reinterpret_cast<volatile unsigned long long *>(out)) atomicMax(out, bits);
     }
 }
+// displacement level of an atom: ceil(|x - site| / 0.01a), rounded up like the host's pick_list (+1e-6 A), capped at 255
+__device__ __forceinline__ unsigned char disp_level(const double dist2, const double a) {
+    const double l = ceil((sqrt(dist2) + 1e-6) / (0.01 * a));
+    return (unsigned char)(l > 255.0 ? 255 : (int)l);
+}
 // squared displacement of the atom from its ideal site after the drift (0 for vacant sites).
 // KICK2: the second half-kick of the step that just finished (NewtonMotion::secondstep, same f) is applied first --
 // inside a multi-step call the two streaming passes over v and f become one (bit-identical: the same two rounded adds)
@@ -198,7 +203,7 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
     int cx, y, z;
     const int d = owned_cell_to_dev(g, p, c, cx, y, z);
     const int t = s.type[d];
-    if (t < 0) return 0.0;
+    if (t < 0) { s.ulev[d] = 0; return 0.0; }
 
     const double cm = vp.c[t];
     double x[3];
@@ -226,6 +231,7 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
         if (slot < runaway_cap) runaway_sites[slot] = d;
         else atomicExch(&counters[3], 1);
     }
+    s.ulev[d] = disp_level(dist, g.a);
     return dist;
 }
 
@@ -405,6 +411,7 @@ k_max_displacement(const Geo g, const Soa s, unsigned long long *__restrict__ ou
         const double ex = s.x[0][d] - xt, ey = s.x[1][d] - yt, ez = s.x[2][d] - zt;
         dist = ex * ex + ey * ey + ez * ez;
     }
+    if (d < g.n_ext) s.ulev[d] = disp_level(dist, g.a);
     report_max(dist, out);
 }
 

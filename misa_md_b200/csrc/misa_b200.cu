@@ -17,7 +17,7 @@
 #include "nccl_dl.cuh"
 #include "inter.cuh"
 #include "eam_smem.cuh"
-#include "eam_fast.cuh"
+#include "eam_sym.cuh"
 #include "dump.cuh"
 #include "world.cuh"
 
@@ -92,6 +92,7 @@ static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off, int 
 static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes);
 static inline bool no_vacancy(const misa_b200_ctx *c);
 static bool dilute_ok(const misa_b200_ctx *c, const StagePlan &sp, bool accum);
+static bool sym_active(const misa_b200_ctx *c, const StagePlan &sp);
 static int smem_kernels_init(int optin) {
     static bool done = false;
     if (done) return 0;
@@ -112,6 +113,8 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_rho_f<true, true, true, false, true>)); OPTIN((k_rho_f<true, true, false, false, true>));
     OPTIN((k_rho_f<true, false, true, false, true>)); OPTIN((k_rho_f<true, false, false, false, true>));
     OPTIN((k_force_f<true, true, false, true>)); OPTIN((k_force_f<true, false, false, true>));
+    OPTIN((k_rho_a<true, false>)); OPTIN((k_rho_a<false, false>)); OPTIN((k_rho_a<true, true>)); OPTIN((k_rho_a<false, true>));
+    OPTIN((k_force_a<true, false>)); OPTIN((k_force_a<false, false>)); OPTIN((k_force_a<true, true>)); OPTIN((k_force_a<false, true>));
 #undef OPTIN
     done = true;
     return 0;
@@ -194,7 +197,8 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     for (int k = 0; k < 3; k++) c->s.x[k] = c->d_xyzd + (size_t)k * c->xyzd_stride;
     c->s.df = c->d_xyzd + 3 * (size_t)c->xyzd_stride;
     for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.v[k], n)); TRY(dmalloc(&c->s.f[k], n)); }
-    TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n));
+    TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n)); TRY(dmalloc(&c->s.ulev, n));
+    CU(cudaMemset(c->s.ulev, 0xff, n));
     for (int k = 0; k < 3; k++) { CU(cudaMemset(c->s.v[k], 0, n * 8)); CU(cudaMemset(c->s.f[k], 0, n * 8)); }
     CU(cudaMemset(c->s.rho, 0, n * 8)); CU(cudaMemset(c->s.type, 0xff, n)); CU(cudaMemset(c->s.id, 0, n * 8));
     {
@@ -307,7 +311,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     if (c->tex_all) cudaDestroyTextureObject(c->tex_all);
     cudaFree(c->d_xyzd);
     for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
-    cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id);
+    cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id); cudaFree(c->s.ulev);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -319,6 +323,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
     cudaFree(c->d_minor); cudaFree(c->d_minor_count); cudaFree(c->d_mcount); cudaFree(c->d_mentry);
+    cudaFree(c->d_lo_tab); cudaFree(c->d_pair);
     cudaFree(c->d_dump); cudaFree(c->d_dump_base); cudaFree(c->d_dump_total); cudaFree(c->d_dump_count); cudaFreeHost(c->h_dump_total);
     inter_free(c);
     for (int k = 0; k < MISA_B200_K_COUNT; k++) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
@@ -337,12 +342,16 @@ static int ref_off_to_dev(long long off, int p, long long H) {
     return (int)((off + 1) / 2 - H);
 }
 // decode a reference offset into (dx, dy, dz) and return the squared SITE separation in units of a^2
-static double off_site_r2(long long off, int p, const Geo &g) {
+static void off_decode(long long off, const Geo &g, long long &dx, long long &dy, long long &dz) {
     const long long sx = 2LL * g.sxc, sy = g.sy;
-    long long dx = ((off % sx) + sx + sx / 2) % sx - sx / 2;
-    long long r = (off - dx) / sx;
-    long long dy = ((r % sy) + sy + sy / 2) % sy - sy / 2;
-    long long dz = (r - dy) / sy;
+    dx = ((off % sx) + sx + sx / 2) % sx - sx / 2;
+    const long long r = (off - dx) / sx;
+    dy = ((r % sy) + sy + sy / 2) % sy - sy / 2;
+    dz = (r - dy) / sy;
+}
+static double off_site_r2(long long off, int p, const Geo &g) {
+    long long dx, dy, dz;
+    off_decode(off, g, dx, dy, dz);
     const double half = (dx & 1) ? (p == 0 ? 0.5 : -0.5) : 0.0; // odd dx switches sub-lattice
     const double X = 0.5 * (double)dx, Y = (double)dy + half, Z = (double)dz + half;
     return X * X + Y * Y + Z * Z;
@@ -359,23 +368,89 @@ static int upload_offsets(misa_b200_ctx *c) {
     // cutoff -- are in range for practically every atom and are evaluated without a branch (eam_fast.cuh)
     std::vector<double> site_r2[2];
     {
-        const double near_lim = c->dom.cutoff_radius_factor - 0.1;
-        int near[2] = {0, 0};
+        // near: shells that reach inside the cutoff at thermal displacements -- up to 0.05a OUTSIDE it, which takes in the
+        // <200> shell of bcc (2.0a against crf = 1.961: 16 % of those pairs are in range at 300 K, i.e. practically every
+        // warp-wide vote of the far loop was true for them anyway)
+        const double near_lim = c->dom.cutoff_radius_factor + 0.05;
+        int near[2] = {0, 0}, half[2] = {0, 0};
+        std::vector<long long> sorted_ref[2];
         for (int p = 0; p < 2; p++) {
             std::vector<int> perm(c->n_full);
             std::vector<double> r2(c->n_full);
             for (int q = 0; q < c->n_full; q++) { perm[q] = q; r2[q] = off_site_r2(c->ref_off[p][q], p, g); }
             // near group first; inside a group keep the reference's order (ascending memory offset: consecutive
             // iterations then touch neighbouring lines, which is what keeps the L1 hit rate up)
-            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return (r2[a] < near_lim * near_lim) > (r2[b] < near_lim * near_lim); });
+            // ... and inside the near group the UPPER half first: the pair-symmetric passes (eam_sym.cuh) evaluate only
+            // those. "Upper" is the sign of the real-space site separation (z, then y, then x) -- the same 29 vectors for
+            // both sub-lattices of the Bravais lattice, whereas the reference's index-order half list
+            // (neighbour_index.inl:79-92) splits the near shells 21 : 37 between even and odd x. Any antisymmetric
+            // choice visits every pair exactly once; the per-atom sums do not depend on it.
+            auto upper = [&](int q) {
+                long long dx, dy, dz;
+                off_decode(c->ref_off[p][q], g, dx, dy, dz);
+                const int h2 = (dx & 1) ? (p == 0 ? 1 : -1) : 0;             // twice the half-cell shift of an odd dx
+                const long long X = dx, Y = 2 * dy + h2, Z = 2 * dz + h2;     // twice the separation in units of a
+                return Z > 0 || (Z == 0 && (Y > 0 || (Y == 0 && X > 0)));
+            };
+            auto cls = [&](int q) { return r2[q] < near_lim * near_lim ? (upper(q) ? 0 : 1) : 2; };
+            // far group: by site separation (shell by shell, reference order inside a shell), so that every pruned list is
+            // a prefix of this one (eam_smem.cuh:list_len)
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+                if (cls(a) != cls(b)) return cls(a) < cls(b);
+                return cls(a) == 2 && r2[a] < r2[b];
+            });
             site_r2[p].resize(c->n_full);
+            sorted_ref[p].resize(c->n_full);
             for (int q = 0; q < c->n_full; q++) {
                 full[(size_t)p * c->n_full + q] = ref_off_to_dev(c->ref_off[p][perm[q]], p, g.H);
                 site_r2[p][q] = r2[perm[q]];
-                if (site_r2[p][q] < near_lim * near_lim) near[p]++;
+                sorted_ref[p][q] = c->ref_off[p][perm[q]];
+                if (cls(perm[q]) < 2) near[p]++;
+                if (cls(perm[q]) == 0) half[p]++;
             }
         }
         c->near_full = std::min(near[0], near[1]);
+        // pair-symmetric passes: both parities must agree on the split, every lower near offset of parity pj must be the
+        // mirror of an upper near offset of the neighbour's parity, and the sites around the owned box that own such a
+        // pair must exist in the ghost shell
+        c->n_half = 0;
+        cudaFree(c->d_lo_tab); c->d_lo_tab = nullptr;
+        if (near[0] == near[1] && half[0] == half[1] && 2 * half[0] == near[0] && half[0] > 0) {
+            const int nh = half[0];
+            std::vector<int2> lo(2 * (size_t)nh);
+            bool ok = true;
+            int elo[3] = {0, 0, 0}, ehi[3] = {0, 0, 0};
+            for (int pj = 0; pj < 2 && ok; pj++)
+                for (int m = 0; m < nh && ok; m++) {
+                    const long long o = sorted_ref[pj][nh + m];            // lower near entry: i = j + o
+                    const int pi = pj ^ (int)(o & 1);
+                    int slot = -1;
+                    for (int k = 0; k < nh; k++) if (sorted_ref[pi][k] == -o) slot = k;
+                    if (slot < 0) { ok = false; break; }
+                    lo[(size_t)pj * nh + m] = make_int2(full[(size_t)pj * c->n_full + nh + m], slot);
+                    long long dx, dy, dz;
+                    off_decode(o, g, dx, dy, dz);
+                    const long long dc[3] = {(pj + dx) >> 1, dy, dz};      // cells from j to its lower neighbour
+                    for (int k = 0; k < 3; k++) { elo[k] = (int)std::max<long long>(elo[k], -dc[k]); ehi[k] = (int)std::max<long long>(ehi[k], dc[k]); }
+                }
+            const int gh[3] = {g.gx, g.gy, g.gz};
+            for (int k = 0; k < 3; k++) ok = ok && elo[k] <= gh[k] && ehi[k] <= gh[k];
+            if (ok) {
+                c->n_half = nh;
+                for (int k = 0; k < 3; k++) { c->sym_lo[k] = elo[k]; c->sym_hi[k] = ehi[k]; }
+                TRY(dmalloc(&c->d_lo_tab, lo.size()));
+                CU(cudaMemcpy(c->d_lo_tab, lo.data(), lo.size() * sizeof(int2), cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    // prefix lengths of the sorted full list by PAIR displacement level: sites closer than (crf + 0.01 L) a
+    for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) {
+        const double lim = c->dom.cutoff_radius_factor + 0.01 * L + 1e-9;
+        int n[2] = {0, 0};
+        for (int p = 0; p < 2; p++)
+            for (int q = 0; q < c->n_full; q++)
+                if (q < c->near_full || site_r2[p][q] < lim * lim) n[p] = q + 1;
+        c->prefix_n[L] = std::max(n[0], n[1]);
     }
     // pairs of LATTICE atoms can only be within the cutoff if their sites are closer than crf + 2*dmax/a;
     // atom::decide keeps dmax <= 0.2a (reference src/atom.cpp:42), the device measures the actual value.
@@ -645,6 +720,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "novac")) c->opt_novac = value;
     else if (!strcmp(name, "fast")) c->opt_fast = value;
     else if (!strcmp(name, "dilute")) c->opt_dilute = value;
+    else if (!strcmp(name, "sym")) c->opt_sym = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
@@ -673,6 +749,8 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
     else if (!strcmp(name, "smem_bytes")) *value = planned ? (double)sb : 0.0;
     else if (!strcmp(name, "dilute")) *value = planned && dilute_ok(c, sp, false) ? 1 : 0;
     else if (!strcmp(name, "n_minor")) *value = c->minor_valid ? c->n_minor : -1;
+    else if (!strcmp(name, "n_half")) *value = c->n_half;
+    else if (!strcmp(name, "sym")) *value = planned && sym_active(c, sp) ? 1 : 0;
     else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
     return 0;
 }
@@ -941,12 +1019,19 @@ static RegionList make_regions(const Geo &g, int which) {
 static LevelSel make_levelsel(const misa_b200_ctx *c, const unsigned long long *dmax2) {
     LevelSel ls;
     memset(&ls, 0, sizeof ls);
-    if (!dmax2 || !c->opt_prune) return ls;
+    ls.host_level = -1;
+    ls.n_full = c->n_full; ls.near_full = c->near_full;
+    ls.step = 0.01 * c->geo.a;
+    ls.ulev = c->s.ulev;
+    for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) ls.prefix[L] = c->prefix_n[L];
+    if (!c->opt_prune) return ls;
+    if (!dmax2) {   // the host's knowledge (serial path): same rounding as pick_list
+        if (c->dmax_valid) ls.host_level = (int)std::min(ceil((sqrt(c->dmax2) + 1e-6) / ls.step), 1000.0);
+        return ls;
+    }
     ls.dmax2_bits = dmax2;
     ls.levels = c->d_off_levels; ls.full = c->d_off_full;
     for (int L = 0; L < misa_b200_ctx::kLevels; L++) { ls.n[L] = c->level_n[L]; ls.near_[L] = c->level_near[L]; ls.ofs[L] = (int)c->level_ofs[L]; }
-    ls.n_full = c->n_full; ls.near_full = c->near_full;
-    ls.step = 0.01 * c->geo.a;
     return ls;
 }
 struct StencilOpt {                 // how one stencil launch deviates from "whole sub-box, host-chosen list, main stream"
@@ -954,6 +1039,49 @@ struct StencilOpt {                 // how one stencil launch deviates from "who
     const unsigned long long *dmax2 = nullptr;
     int reserve_sms = 0;            // leave this many SMs free (the persistent CTAs would otherwise starve the exchange kernels on stream2)
 };
+
+// ---- pair-symmetric passes (eam_sym.cuh) --------------------------------------------------------------------------
+// One species (or a dilute alloy, whose main loop is the majority species'), overwrite semantics, the whole sub-box in
+// one launch (the interior / boundary split of the overlapped exchange keeps the full-list kernels).
+static bool sym_ok(const misa_b200_ctx *c, const StagePlan &sp, bool accum, const StencilOpt &so) {
+    if (!c->opt_sym || c->n_half <= 0 || !c->d_lo_tab || accum || so.region != 0) return false;
+    return sp.single >= 0 || dilute_ok(c, sp, accum);
+}
+static bool sym_active(const misa_b200_ctx *c, const StagePlan &sp) { return sym_ok(c, sp, false, StencilOpt()); }
+static int sym_scratch(misa_b200_ctx *c) {
+    const size_t need = (size_t)c->n_half * (((size_t)c->geo.n_ext + 31) / 32 * 32);
+    if (c->pair_elems >= need) return 0;
+    cudaFree(c->d_pair); c->d_pair = nullptr; c->pair_elems = 0;
+    TRY(dmalloc(&c->d_pair, need));
+    c->pair_elems = need;
+    return 0;
+}
+// pass-A work: the owned box (region 0) + the slabs of ghost sites around it that own pairs with owned atoms
+static RegionList make_regions_sym(const misa_b200_ctx *c) {
+    const Geo &g = c->geo;
+    const int *lo = c->sym_lo, *hi = c->sym_hi;
+    RegionList rl;
+    memset(&rl, 0, sizeof rl);
+    auto add = [&](int x0, int y0, int z0, int nx, int ny, int nz) {
+        if (nx <= 0 || ny <= 0 || nz <= 0) return;
+        Region &r = rl.r[rl.n++];
+        r.x0 = x0; r.y0 = y0; r.z0 = z0; r.nx = nx; r.ny = ny; r.nz = nz; r.u0 = rl.units;
+        rl.units += ((long long)nx * ny * nz + 31) / 32;
+    };
+    const int wx = g.nx + lo[0] + hi[0], wy = g.ny + lo[1] + hi[1];
+    add(0, 0, 0, g.nx, g.ny, g.nz);
+    add(-lo[0], -lo[1], -lo[2], wx, wy, lo[2]);
+    add(-lo[0], -lo[1], g.nz, wx, wy, hi[2]);
+    add(-lo[0], -lo[1], 0, wx, lo[1], g.nz);
+    add(-lo[0], g.ny, 0, wx, hi[1], g.nz);
+    add(-lo[0], 0, 0, lo[0], g.ny, g.nz);
+    add(g.nx, 0, 0, hi[0], g.ny, g.nz);
+    return rl;
+}
+static int sym_b_grid(const misa_b200_ctx *c, const RegionList &rl) {
+    const long long blocks = (2 * rl.units + SYM_B_THREADS / 32 - 1) / (SYM_B_THREADS / 32);
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)std::max(c->sm_count, 1) * 16));
+}
 
 static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilOpt &so = StencilOpt()) {
     const Geo &g = c->geo;
@@ -972,9 +1100,32 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const RegionList rl = make_regions(g, so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;
+        if (sym_ok(c, sp, accum, so)) {
+            TRY(sym_scratch(c));
+            const bool dil = sp.single < 0;
+            const MinorList ml = dil ? minor_list(c) : MinorList();
+            const SymPlan sy = {c->d_pair, c->d_lo_tab, c->n_half, g.n_ext};
+            const RegionList ra = make_regions_sym(c);
+#define RHO_A(N, D) k_rho_a<N, D><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, ra, ls, ml, sy)
+            if (novac) { if (dil) RHO_A(true, true); else RHO_A(true, false); }
+            else { if (dil) RHO_A(false, true); else RHO_A(false, false); }
+#undef RHO_A
+            CU(cudaGetLastError());
+            const int gb = sym_b_grid(c, rl);
+            const size_t lb = 2 * (size_t)c->n_half * sizeof(int2);
+#define RHO_B(N, F, D) k_rho_b<N, F, D><<<gb, SYM_B_THREADS, lb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, rl, ls, sy)
+#define RHO_BF(N, D) do { if (fuse_df) RHO_B(N, true, D); else RHO_B(N, false, D); } while (0)
+            if (novac) { if (dil) RHO_BF(true, true); else RHO_BF(true, false); }
+            else { if (dil) RHO_BF(false, true); else RHO_BF(false, false); }
+#undef RHO_BF
+#undef RHO_B
+            c->launches += 2;
+            CU(cudaGetLastError());
+            return 0;
+        }
         if (dilute_ok(c, sp, accum)) {
             const MinorList ml = minor_list(c);
-#define RHO_D(N, F) k_rho_f<true, N, F, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, ml)
+#define RHO_D(N, F) k_rho_f<true, N, F, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml)
             if (novac) { if (fuse_df) RHO_D(true, true); else RHO_D(true, false); }
             else { if (fuse_df) RHO_D(false, true); else RHO_D(false, false); }
 #undef RHO_D
@@ -982,7 +1133,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
             CU(cudaGetLastError());
             return 0;
         }
-#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, MinorList())
+#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList())
 #define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
         if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
 #undef RHO_FA
@@ -1041,6 +1192,36 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     Slot sl(c, MISA_B200_K_FORCE);
     StagePlan sp;
     size_t sb;
+    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && sym_ok(c, sp, accum, so)) {
+        TRY(sym_scratch(c));
+        const int grid = std::max(1, c->sm_count - so.reserve_sms);
+        const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+        const RegionList rl = make_regions(g, 0), ra = make_regions_sym(c);
+        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const bool dil = sp.single < 0, novac = no_vacancy(c);
+        const MinorList ml = dil ? minor_list(c) : MinorList();
+        const SymPlan sy = {c->d_pair, c->d_lo_tab, c->n_half, g.n_ext};
+#define FORCE_A(N, D) k_force_a<N, D><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, ra, ls, ml, sy)
+        if (novac) { if (dil) FORCE_A(true, true); else FORCE_A(true, false); }
+        else { if (dil) FORCE_A(false, true); else FORCE_A(false, false); }
+#undef FORCE_A
+        CU(cudaGetLastError());
+        const int gb = sym_b_grid(c, rl);
+        const size_t lb = 2 * (size_t)c->n_half * sizeof(int2);
+#define FORCE_B(N, D) k_force_b<N, D><<<gb, SYM_B_THREADS, lb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, rl, ls, sy, sp.staged_id[0])
+        if (novac) { if (dil) FORCE_B(true, true); else FORCE_B(true, false); }
+        else { if (dil) FORCE_B(false, true); else FORCE_B(false, false); }
+#undef FORCE_B
+        c->launches += 2;
+        CU(cudaGetLastError());
+        if (dil && c->n_minor > 0) {
+            const int mgrid = std::min((c->n_minor + 7) / 8, std::max(1, c->sm_count) * 8);
+            k_force_minor<<<mgrid, 256, 0, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, ls, c->d_minor, c->n_minor, tex);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        return 0;
+    }
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
@@ -1048,8 +1229,8 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const LevelSel ls = make_levelsel(c, so.dmax2);
         const MinorList ml = minor_list(c);
         if (rl.units > 0) {
-            if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, ml);
-            else k_force_f<true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, ml);
+            if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml);
+            else k_force_f<true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml);
             c->launches++;
             CU(cudaGetLastError());
         }
@@ -1072,8 +1253,8 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const RegionList rl = make_regions(g, so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;
-#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, MinorList()); \
-                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, n_near, tex, rl, ls, MinorList()); } while (0)
+#define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); \
+                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); } while (0)
         if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
 #undef FORCE_F
         c->launches++;

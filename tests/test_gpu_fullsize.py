@@ -67,12 +67,13 @@ def test_compat_hooks_equal_resident_kernels(big):
     ctx.eam_df_calc(host)
     own = cm.owned(ctx, host)
     ref = cm.owned(ctx, got)
-    assert cm.rel_err(own["rho"], ref["rho"]) < 1e-13
-    assert cm.rel_err(own["df"], ref["df"]) < 1e-13
+    # the hooks accumulate with the full-list kernels, the resident step takes the pair-symmetric passes: other summation order
+    assert cm.rel_err(own["rho"], ref["rho"]) < 1e-12
+    assert cm.rel_err(own["df"], ref["df"]) < 1e-12
     h3 = host.reshape(ctx.ext_shape)
     h3["df"][...] = got.reshape(ctx.ext_shape)["df"]  # the host's df halo (DfEmbedPacker) fills the ghosts
     ctx.eam_force_calc(host)
-    assert cm.rel_err(cm.owned(ctx, host)["f"], ref["f"]) < 1e-12
+    assert cm.rel_err(cm.owned(ctx, host)["f"], ref["f"]) < 1e-11
     ctx.host_unregister(host)
     ctx.upload(got)  # hooks overwrote the resident state with `host`; restore for the following tests
     ctx.prepare()
