@@ -395,6 +395,7 @@ def run_b200(args):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "state": {"runaways_last_step": th["runaways"], "inter_atoms": th["n_inter"], "equil_steps": args.equil,
                   "world_build_ms": 1e3 * t_build, "stencil_offsets": int(ctx.query("n_off")), "stencil_offsets_full": int(ctx.query("n_full")),
+                  "ghost_exchange": ("periodic fill in place" if n_gpus == 1 else "direct push over NVLink peer memory (csrc/p2p.cuh)" if ctx.query("p2p") else "staged NCCL send/recv"),
                   "max_displacement_A": ctx.query("dmax"), "temperature_K": th["mvv"] * 1.0364269e-4 / ((3 * th["n_atoms"] - 3) * 8.617343e-5)},
     }
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:

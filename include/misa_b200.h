@@ -101,6 +101,14 @@ int misa_b200_plan_offsets(const misa_b200_domain *dom, int cut_lattice, double 
                            int64_t *out, size_t cap, size_t *n);
 int misa_b200_plan_halo(const misa_b200_domain *dom, int dim, int dir, int64_t *send, int64_t *recv, size_t cap,
                         size_t *n, double shift[3]);
+/* Host-only: the three staged exchanges above composed into ONE ghost <- owned map (what the direct NVLink push of
+ * the multi-GPU path applies, csrc/p2p.cuh). Entry i: site dst[i] of this sub-box receives site src[i] of the sub-box
+ * at offset (sx, sy, sz), code[i] = (sx+1) + 3 (sy+1) + 9 (sz+1); all sub-boxes have the same shape, so read backwards
+ * it is what this sub-box pushes to the sub-box at the opposite offset, with image shift shift[code] added. Indices
+ * in the reference's index space. Replaces nothing in the reference: it is the closed form of
+ * comm::neiSendReceive x 3 with LatPacker (src/atom/atom_list.cpp:51-57, src/pack/lat_particle_packer.cpp:97-139). */
+int misa_b200_plan_push(const misa_b200_domain *dom, int64_t *dst, int64_t *src, int8_t *code, size_t cap, size_t *n,
+                        double shift[27][3]);
 /* n_types species in atom_type enum order (Fe, Cu, Ni); phi is n_types*n_types, symmetric. */
 int misa_b200_set_potential(misa_b200_ctx *ctx, int n_types, const misa_b200_table *electron_density,
                             const misa_b200_table *embedded, const misa_b200_table *phi);

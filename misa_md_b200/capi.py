@@ -20,7 +20,7 @@ K_COUNT = len(K_NAMES)
 EXPORTS = [
     "misa_b200_env_init", "misa_b200_env_clean", "misa_b200_device_count", "misa_b200_last_error",
     "misa_b200_create", "misa_b200_destroy", "misa_b200_set_neighbour_offsets", "misa_b200_make_neighbour_offsets",
-    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_set_potential",
+    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_plan_push", "misa_b200_set_potential",
     "misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc",
     "misa_b200_site_count", "misa_b200_host_register", "misa_b200_host_unregister",
     "misa_b200_upload_atoms", "misa_b200_download_atoms", "misa_b200_upload_inter", "misa_b200_download_inter",
@@ -83,6 +83,7 @@ def load(build=True):
     L.misa_b200_get_neighbour_offsets.argtypes = [vp, i, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.misa_b200_plan_offsets.argtypes = [C.POINTER(Domain), i, d, i, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.misa_b200_plan_halo.argtypes = [C.POINTER(Domain), i, i, i64p, i64p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(d * 3)]
+    L.misa_b200_plan_push.argtypes = [C.POINTER(Domain), i64p, i64p, C.POINTER(C.c_int8), C.c_size_t, C.POINTER(C.c_size_t), vp]
     L.misa_b200_set_potential.argtypes = [vp, i, C.POINTER(Table), C.POINTER(Table), C.POINTER(Table)]
     for fn in ("misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc"):
         getattr(L, fn).argtypes = [vp, vp, d]
@@ -182,6 +183,22 @@ def plan_halo(dom, dim, direction):
     p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
     _ck(L.misa_b200_plan_halo(C.byref(dom), dim, direction, p(send), p(recv), n.value, C.byref(n), C.byref(shift)))
     return send, recv, np.array(list(shift))
+
+
+def plan_push(dom):
+    """Host-only: the staged exchanges composed into one ghost <- owned map: (dst, src, code, shift[27][3]); see
+    include/misa_b200.h:misa_b200_plan_push."""
+    L = load()
+    n = C.c_size_t()
+    _ck(L.misa_b200_plan_push(C.byref(dom), None, None, None, 0, C.byref(n), None))
+    dst = np.zeros(n.value, dtype=np.int64)
+    src = np.zeros(n.value, dtype=np.int64)
+    code = np.zeros(n.value, dtype=np.int8)
+    shift = np.zeros((27, 3), dtype=np.float64)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    _ck(L.misa_b200_plan_push(C.byref(dom), p(dst), p(src), code.ctypes.data_as(C.POINTER(C.c_int8)), n.value, C.byref(n),
+                              shift.ctypes.data_as(C.c_void_p)))
+    return dst, src, code, shift
 
 
 class Context:

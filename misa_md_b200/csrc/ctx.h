@@ -62,6 +62,16 @@ struct HaloList {          // one (dim, dir) message
     double shift[3] = {0, 0, 0};
 };
 
+// direct ghost push over NVLink peer memory (p2p.cuh): per direction code the destination sub-box's arrays and flags
+struct P2pPeers {
+    double *xyzd[27];              // the destination's x|y|z|df block
+    int8_t *type[27];
+    unsigned long long *flags[27];
+    double shift[27][3];           // periodic image shift of the group
+    long long stride;              // field stride of the block (doubles)
+    unsigned int mask;             // direction codes in use
+};
+
 struct misa_b200_ctx {
     misa_b200_domain dom;
     Geo geo;
@@ -131,6 +141,17 @@ struct misa_b200_ctx {
     int8_t *d_ghost_shift = nullptr;      // per ghost site: shift code (3 x {-1,0,1}) packed
     double *d_sendbuf[2] = {nullptr, nullptr}, *d_recvbuf[2] = {nullptr, nullptr};
     size_t halo_buf_elems = 0;
+    // direct push of the composed ghost <- owned map into the neighbours' HBM (p2p.cuh)
+    int opt_p2p = -1;                     // -1 / 1: whenever every surrounding sub-box is peer-mapped on this node; 0: NCCL send/recv
+    bool p2p_active = false;
+    int n_push = 0;
+    int *d_push_dst = nullptr, *d_push_src = nullptr;
+    int8_t *d_push_code = nullptr;
+    bool push_code_used[27] = {false};
+    P2pPeers p2p{};
+    unsigned long long *d_flags = nullptr, p2p_epoch = 0, p2p_ready_sent = 0;   // flags: [0,27) ready, [32,59) arrive, [63] CTA counter
+    unsigned int *h_p2p_err = nullptr, *d_p2p_err = nullptr;
+    std::vector<void *> p2p_opened;
     // integrator
     double dt = 0.001;
     double dt_inv_m[MISA_MAX_TYPES] = {0, 0, 0};

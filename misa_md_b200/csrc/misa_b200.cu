@@ -128,6 +128,7 @@ static int dmalloc(T **p, size_t n) {
     CU(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
     return 0;
 }
+#include "p2p.cuh"   // needs dmalloc
 
 static int geo_from_domain(const misa_b200_domain *dom, Geo &g) {
     g.nx = dom->sub_box_lattice_size[0]; g.ny = dom->sub_box_lattice_size[1]; g.nz = dom->sub_box_lattice_size[2];
@@ -174,6 +175,59 @@ static void build_halo_lists_host(const Geo &g, std::vector<int> send[3][2], std
             fill(send[d][dir], slo, shi);
             fill(recv[d][dir], rlo, rhi);
         }
+}
+
+// Compose the three staged exchanges into one ghost <- owned map. Every sub-box has this shape and runs these stages, so
+// "site b receives what the sender held at site a" chains symbolically: code = direction of the sub-box the value
+// ORIGINATES from, (sx+1) + 3 (sy+1) + 9 (sz+1), src = its site there (device index space). Entries come out grouped by
+// code, destination ascending inside a group.
+static void compose_push_map(const std::vector<int> send[3][2], const std::vector<int> recv[3][2], size_t n_ext, std::vector<int> &dst,
+                             std::vector<int> &src, std::vector<int8_t> &codes) {
+    std::vector<int> src_of(n_ext), code(n_ext, 13); // 13 = (0+1) + 3*(0+1) + 9*(0+1)
+    for (size_t i = 0; i < n_ext; i++) src_of[i] = (int)i;
+    static const int mul[3] = {1, 3, 9};
+    dst.clear();
+    for (int d = 0; d < 3; d++)
+        for (int dir = 0; dir < 2; dir++)
+            for (size_t i = 0; i < send[d][dir].size(); i++) {
+                const int a = send[d][dir][i], b = recv[d][dir][i];
+                src_of[b] = src_of[a];
+                code[b] = code[a] + mul[d] * (dir == 0 ? 1 : -1);
+                dst.push_back(b);
+            }
+    std::sort(dst.begin(), dst.end(), [&](int a, int b) { return code[a] != code[b] ? code[a] < code[b] : a < b; });
+    dst.erase(std::unique(dst.begin(), dst.end()), dst.end());
+    src.resize(dst.size());
+    codes.resize(dst.size());
+    for (size_t i = 0; i < dst.size(); i++) { src[i] = src_of[dst[i]]; codes[i] = (int8_t)code[dst[i]]; }
+}
+// image shift of group `code` pushed by the sub-box at grid_coord: what the staged path adds hop by hop
+// (reference src/pack/lat_particle_packer.cpp:22-32)
+static void push_shift(const misa_b200_domain *dom, int code, double shift[3]) {
+    const int s[3] = {code % 3 - 1, (code / 3) % 3 - 1, code / 9 - 1};
+    for (int d = 0; d < 3; d++) {
+        shift[d] = 0.0;
+        if (s[d] == 1 && dom->grid_coord[d] == 0) shift[d] = dom->meas_global_length[d];
+        if (s[d] == -1 && dom->grid_coord[d] == dom->grid_size[d] - 1) shift[d] = -dom->meas_global_length[d];
+    }
+}
+extern "C" int misa_b200_plan_push(const misa_b200_domain *dom, int64_t *dst, int64_t *src, int8_t *code, size_t cap, size_t *n,
+                                   double shift[27][3]) {
+    REQ(dom && n, MISA_B200_EINVAL, "misa_b200_plan_push: bad argument");
+    Geo g;
+    REQ(geo_from_domain(dom, g) == 0, MISA_B200_EINVAL, "misa_b200_plan_push: bad sub-box sizes");
+    std::vector<int> s[3][2], r[3][2], d_, s_;
+    std::vector<int8_t> c_;
+    build_halo_lists_host(g, s, r);
+    compose_push_map(s, r, (size_t)g.n_ext, d_, s_, c_);
+    *n = d_.size();
+    for (size_t i = 0; i < std::min(cap, *n); i++) {
+        if (dst) dst[i] = dev_to_ref(d_[i], g.H);
+        if (src) src[i] = dev_to_ref(s_[i], g.H);
+        if (code) code[i] = c_[i];
+    }
+    if (shift) for (int k = 0; k < 27; k++) push_shift(dom, k, shift[k]);
+    return MISA_B200_OK;
 }
 
 extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out) {
@@ -258,29 +312,26 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
         }
     c->halo_buf_elems = max_n * 4;
     for (int dir = 0; dir < 2; dir++) { TRY(dmalloc(&c->d_sendbuf[dir], c->halo_buf_elems)); TRY(dmalloc(&c->d_recvbuf[dir], c->halo_buf_elems)); }
-    if (c->all_self) {
-        // compose the three staged self-exchanges into one ghost <- owned map
-        std::vector<int> src_of(n), code(n, 13); // 13 = (0+1) + 3*(0+1) + 9*(0+1)
-        for (size_t i = 0; i < n; i++) src_of[i] = (int)i;
-        std::vector<int> dst_list;
-        static const int mul[3] = {1, 3, 9};
-        for (int d = 0; d < 3; d++)
-            for (int dir = 0; dir < 2; dir++)
-                for (size_t i = 0; i < send[d][dir].size(); i++) {
-                    const int a = send[d][dir][i], b = recv[d][dir][i];
-                    src_of[b] = src_of[a];
-                    code[b] = code[a] + mul[d] * (dir == 0 ? 1 : -1);
-                    dst_list.push_back(b);
-                }
-        std::sort(dst_list.begin(), dst_list.end());
-        std::vector<int> srcs(dst_list.size());
-        std::vector<int8_t> codes(dst_list.size());
-        for (size_t i = 0; i < dst_list.size(); i++) { srcs[i] = src_of[dst_list[i]]; codes[i] = (int8_t)code[dst_list[i]]; }
-        c->n_ghost_map = (int)dst_list.size();
-        TRY(dmalloc(&c->d_ghost_dst, dst_list.size())); TRY(dmalloc(&c->d_ghost_src, dst_list.size())); TRY(dmalloc(&c->d_ghost_shift, dst_list.size()));
-        CU(cudaMemcpy(c->d_ghost_dst, dst_list.data(), dst_list.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(c->d_ghost_src, srcs.data(), srcs.size() * sizeof(int), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(c->d_ghost_shift, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+    {
+        // 1x1x1 grid: the origin of every ghost is this sub-box itself (k_ghost_fill_*); otherwise the map read backwards is
+        // what this sub-box pushes into its neighbours (p2p.cuh)
+        std::vector<int> dst_list, srcs;
+        std::vector<int8_t> codes;
+        compose_push_map(send, recv, n, dst_list, srcs, codes);
+        if (c->all_self) {
+            c->n_ghost_map = (int)dst_list.size();
+            TRY(dmalloc(&c->d_ghost_dst, dst_list.size())); TRY(dmalloc(&c->d_ghost_src, dst_list.size())); TRY(dmalloc(&c->d_ghost_shift, dst_list.size()));
+            CU(cudaMemcpy(c->d_ghost_dst, dst_list.data(), dst_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->d_ghost_src, srcs.data(), srcs.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->d_ghost_shift, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+        } else {
+            for (int8_t k : codes) c->push_code_used[k] = true;
+            c->n_push = (int)dst_list.size();
+            TRY(dmalloc(&c->d_push_dst, dst_list.size())); TRY(dmalloc(&c->d_push_src, dst_list.size())); TRY(dmalloc(&c->d_push_code, dst_list.size()));
+            CU(cudaMemcpy(c->d_push_dst, dst_list.data(), dst_list.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->d_push_src, srcs.data(), srcs.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->d_push_code, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+        }
     }
     TRY(inter_alloc(c, 1 << 16));
     TRY(dmalloc(&c->d_census, MISA_MAX_TYPES));
@@ -324,6 +375,8 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
     cudaFree(c->d_minor); cudaFree(c->d_minor_count); cudaFree(c->d_mcount); cudaFree(c->d_mentry);
     cudaFree(c->d_lo_tab); cudaFree(c->d_pair);
+    cudaFree(c->d_push_dst); cudaFree(c->d_push_src); cudaFree(c->d_push_code); cudaFree(c->d_flags);
+    if (c->h_p2p_err) cudaFreeHost(c->h_p2p_err);
     cudaFree(c->d_dump); cudaFree(c->d_dump_base); cudaFree(c->d_dump_total); cudaFree(c->d_dump_count); cudaFreeHost(c->h_dump_total);
     inter_free(c);
     for (int k = 0; k < MISA_B200_K_COUNT; k++) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
@@ -721,6 +774,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "fast")) c->opt_fast = value;
     else if (!strcmp(name, "dilute")) c->opt_dilute = value;
     else if (!strcmp(name, "sym")) c->opt_sym = value;
+    else if (!strcmp(name, "p2p")) c->opt_p2p = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
@@ -750,6 +804,8 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
     else if (!strcmp(name, "dilute")) *value = planned && dilute_ok(c, sp, false) ? 1 : 0;
     else if (!strcmp(name, "n_minor")) *value = c->minor_valid ? c->n_minor : -1;
     else if (!strcmp(name, "n_half")) *value = c->n_half;
+    else if (!strcmp(name, "p2p")) *value = c->p2p_active && c->opt_p2p ? 1 : 0;
+    else if (!strcmp(name, "p2p_error")) *value = c->h_p2p_err ? (double)*c->h_p2p_err : 0.0;
     else if (!strcmp(name, "sym")) *value = planned && sym_active(c, sp) ? 1 : 0;
     else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
     return 0;
@@ -769,9 +825,10 @@ extern "C" int misa_b200_comm_init(misa_b200_ctx *c, const void *uid, int rank, 
     NC(g_nccl.CommInitRank(&c->nccl_comm, n_ranks, id, rank));
     c->comm_rank = rank;
     c->comm_size = n_ranks;
-    return 0;
+    return p2p_setup(c);   // ghost exchange by direct stores into the neighbours' HBM when all of them are peer-mapped
 }
 extern "C" int misa_b200_comm_destroy(misa_b200_ctx *c) {
+    if (c) p2p_release(c);
     if (c && c->nccl_comm) {
         g_nccl.CommDestroy(c->nccl_comm);
         c->nccl_comm = nullptr;
@@ -798,6 +855,7 @@ static int halo_forward(misa_b200_ctx *c, bool positions, cudaStream_t st = null
         CU(cudaGetLastError());
         return 0;
     }
+    if (c->p2p_active && c->opt_p2p) return p2p_exchange(c, positions, st);
     for (int d = 0; d < 3; d++) {
         const bool self = c->dom.grid_size[d] == 1;
         const HaloList &h0 = c->halo[d][0], &h1 = c->halo[d][1];
@@ -1462,7 +1520,9 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
     // dimension does, 2 always (tests: also on a 1x1x1 grid).
     int nccl_dims = 0;
     for (int d = 0; d < 3; d++) nccl_dims += c->dom.grid_size[d] > 1;
-    const bool overlap = c->opt_overlap > 1 || (c->opt_overlap == 1 && nccl_dims >= 1) || (c->opt_overlap < 0 && nccl_dims >= 2);
+    // with the direct push (p2p.cuh) an exchange costs tens of microseconds: nothing left to hide
+    const bool p2p = c->p2p_active && c->opt_p2p;
+    const bool overlap = c->opt_overlap > 1 || (c->opt_overlap == 1 && nccl_dims >= 1) || (c->opt_overlap < 0 && nccl_dims >= 2 && !p2p);
     TRY(verlet1_enqueue(c, kick2_in));
     StencilOpt whole, interior, boundary;
     whole.dmax2 = c->d_stepinfo_g + 1;
@@ -1475,6 +1535,9 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
         TRY(launch_rho(c, true, false, whole));
         TRY(halo_forward(c, false));
         TRY(launch_force(c, false, whole));
+        // ghost x and df are free for the next step's two exchanges -- only when that step follows inside this call:
+        // between calls the host may run readers of the ghosts (thermo, dump) that a neighbour's next push must not overtake
+        if (defer_out) TRY(p2p_post_ready(c, 2, c->stream));
     } else {
         CU(cudaEventRecord(c->ev_v1, c->stream));
         CU(cudaStreamWaitEvent(c->stream2, c->ev_v1, 0));

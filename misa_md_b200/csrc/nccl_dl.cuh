@@ -19,10 +19,11 @@ struct NcclApi {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
-static const int kNcclDouble = 8, kNcclInt32 = 2, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2;
+static const int kNcclDouble = 8, kNcclInt32 = 2, kNcclUint64 = 5, kNcclInt8 = 0, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;
 
 static int nccl_load() {
     if (g_nccl.h) return 0;
@@ -44,6 +45,7 @@ static int nccl_load() {
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return 0;

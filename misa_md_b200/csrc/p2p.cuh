@@ -1,0 +1,253 @@
+// misa_md_b200/csrc/p2p.cuh -- ghost exchange as ONE push kernel over NVLink peer memory.
+//
+// The reference moves ghosts in three dependent stages (x, then y, then z: comm::neiSendReceive with LatPacker /
+// DfEmbedPacker, src/atom/atom_list.cpp:51-57, src/pack/lat_particle_packer.cpp:97-139); the stage order is what
+// carries edge and corner sites to diagonal neighbours. Over NCCL that is 3 x (pack kernel, grouped send/recv,
+// unpack kernel) per exchange -- 0.19 ms for positions at 100^3 cells per GPU on a 2x2x2 grid, all latency.
+// On one NVSwitch box every GPU can store into every other GPU's HBM, so the composition of the three stages
+// is applied directly: each ghost site of a sub-box has exactly ONE owned source site in one of the 26 surrounding
+// sub-boxes (misa_b200_create composes the staged send/recv lists into that map; all sub-boxes have the same
+// shape, so the map of "what I receive" read backwards is "what I push"). k_p2p_push_* reads the owned source,
+// adds the periodic image shift the staged path would have added (same rounded add, same bits) and stores straight
+// into the destination's ghost site through an IPC-mapped pointer. Two flag handshakes of system-scope
+// release/acquire stores bracket the push:
+//   ready : receiver -> origin, "everything I enqueued before this exchange (the kernels that read my ghosts) is done"
+//   arrive: origin -> receiver, "my stores into your ghosts are performed"
+// Flags carry the exchange epoch (monotonic), so nothing is ever reset. No data-path collective, no staging buffer.
+#pragma once
+#include <unistd.h>
+#include "ctx.h"
+#include "util.cuh"
+#include "nccl_dl.cuh"
+
+#define P2P_READY 0
+#define P2P_ARRIVE 32
+#define P2P_FLAG_WORDS 64
+#define P2P_SPIN_LIMIT (6000000000LL)   // ~3 s of SM clocks: a peer that never answers ends the wait with an error, not a hang
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// code k = (sx+1) + 3 (sy+1) + 9 (sz+1): the ORIGIN of my ghosts with that code sits at sub-box offset +s from me; I push my
+// own group k to the sub-box at offset -s. Thread k handles direction k.
+__device__ __forceinline__ void p2p_wait(const unsigned long long *w, const unsigned long long epoch, unsigned int *err, const unsigned what) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(w) < epoch)
+        if (clock64() - t0 > P2P_SPIN_LIMIT) { *(volatile unsigned int *)err = what; break; }
+}
+// READY: I am receiver for code k -> tell its origin, which is my destination for code 26 - k, that everything enqueued
+// before this kernel (the readers of my ghosts) is done. `epoch` may lie ahead: "free up to and including exchange epoch".
+__global__ void k_p2p_ready(const P2pPeers pp, const unsigned long long epoch) {
+    const int k = threadIdx.x;
+    if (k >= 27 || !((pp.mask >> k) & 1u)) return;
+    __threadfence_system();
+    st_release_sys(pp.flags[26 - k] + P2P_READY + k, epoch);
+}
+// wait until every origin's stores into my ghosts are performed
+__global__ void k_p2p_wait_arrive(const P2pPeers pp, const unsigned long long epoch, const unsigned long long *__restrict__ my_flags,
+                                  unsigned int *__restrict__ err) {
+    const int k = threadIdx.x;
+    if (k >= 27 || !((pp.mask >> k) & 1u)) return;
+    p2p_wait(my_flags + P2P_ARRIVE + k, epoch, err, 100u + k);
+}
+// head of a push kernel: every destination has freed its ghosts; tail: the LAST CTA to finish tells every destination
+__device__ __forceinline__ void p2p_push_head(const P2pPeers &pp, const unsigned long long epoch, const unsigned long long *my_flags, unsigned int *err) {
+    const int k = threadIdx.x;
+    if (k < 27 && ((pp.mask >> k) & 1u)) p2p_wait(my_flags + P2P_READY + k, epoch, err, 1u + k);
+    __syncthreads();
+}
+__device__ __forceinline__ void p2p_push_tail(const P2pPeers &pp, const unsigned long long epoch, unsigned int *done) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                      // this CTA's stores are performed at their destinations (cumulative over the barrier)
+        last = atomicAdd(done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    const int k = threadIdx.x;
+    if (k == 0) *done = 0;                           // next exchange (stream-ordered after this kernel)
+    __threadfence_system();
+    if (k < 27 && ((pp.mask >> k) & 1u)) st_release_sys(pp.flags[k] + P2P_ARRIVE + k, epoch);
+}
+
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_p2p_push_x(const P2pPeers pp, const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code, const Soa s,
+             const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err) {
+    p2p_push_head(pp, epoch, my_flags, err);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int a = src[i], b = dst[i], k = code[i];
+        double x = s.x[0][a], y = s.x[1][a], z = s.x[2][a];
+        if (pp.shift[k][0] != 0.0) x = __dadd_rn(x, pp.shift[k][0]);
+        if (pp.shift[k][1] != 0.0) y = __dadd_rn(y, pp.shift[k][1]);
+        if (pp.shift[k][2] != 0.0) z = __dadd_rn(z, pp.shift[k][2]);
+        double *P = pp.xyzd[k];
+        P[b] = x; P[pp.stride + b] = y; P[2 * pp.stride + b] = z;
+        pp.type[k][b] = s.type[a];
+    }
+    p2p_push_tail(pp, epoch, done);
+}
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_p2p_push_df(const P2pPeers pp, const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code, const Soa s,
+              const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err) {
+    p2p_push_head(pp, epoch, my_flags, err);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pp.xyzd[code[i]][3 * pp.stride + dst[i]] = s.df[src[i]];
+    p2p_push_tail(pp, epoch, done);
+}
+
+// ---- set-up: exchange IPC handles of the position/df block, the type array and the flag words over the NCCL
+//      communicator, map the (at most 26) surrounding sub-boxes, agree that EVERY rank succeeded --------------------
+struct P2pBlob {
+    int coord[3], size[3], device, ok;
+    long long pid;
+    unsigned long long host;
+    cudaIpcMemHandle_t h_xyzd, h_type, h_flags;
+    void *p_xyzd, *p_type, *p_flags;
+};
+static void push_shift(const misa_b200_domain *dom, int code, double shift[3]);   // misa_b200.cu
+static unsigned long long p2p_host_hash() {
+    char name[256] = {0};
+    gethostname(name, sizeof name - 1);
+    unsigned long long h = 1469598103934665603ULL;
+    for (const char *p = name; *p; p++) h = (h ^ (unsigned char)*p) * 1099511628211ULL;
+    // the boot id separates containers that share a hostname
+    if (FILE *f = fopen("/proc/sys/kernel/random/boot_id", "r")) {
+        int ch;
+        while ((ch = fgetc(f)) != EOF) h = (h ^ (unsigned char)ch) * 1099511628211ULL;
+        fclose(f);
+    }
+    return h;
+}
+static void p2p_release(misa_b200_ctx *c) {
+    for (void *p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    c->p2p_opened.clear();
+    c->p2p_active = false;
+}
+static int p2p_setup(misa_b200_ctx *c) {
+    c->p2p_active = false;
+    if (!c->opt_p2p || c->comm_size <= 1 || !c->nccl_comm || c->n_push <= 0 || !g_nccl.AllGather) return 0;
+    const int n = c->comm_size, me = c->comm_rank;
+    if (!c->d_flags) {
+        TRY(dmalloc(&c->d_flags, P2P_FLAG_WORDS));
+        CU(cudaMemset(c->d_flags, 0, P2P_FLAG_WORDS * sizeof(unsigned long long)));
+        CU(cudaHostAlloc((void **)&c->h_p2p_err, sizeof(unsigned int), cudaHostAllocMapped));
+        *c->h_p2p_err = 0;
+        CU(cudaHostGetDevicePointer((void **)&c->d_p2p_err, c->h_p2p_err, 0));
+    }
+    P2pBlob mine;
+    memset(&mine, 0, sizeof mine);
+    for (int k = 0; k < 3; k++) { mine.coord[k] = c->dom.grid_coord[k]; mine.size[k] = c->dom.sub_box_lattice_size[k]; }
+    mine.device = c->device; mine.pid = (long long)getpid(); mine.host = p2p_host_hash(); mine.ok = 1;
+    mine.p_xyzd = c->d_xyzd; mine.p_type = c->s.type; mine.p_flags = c->d_flags;
+    if (cudaIpcGetMemHandle(&mine.h_xyzd, c->d_xyzd) != cudaSuccess || cudaIpcGetMemHandle(&mine.h_type, c->s.type) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.h_flags, c->d_flags) != cudaSuccess) { mine.ok = 0; cudaGetLastError(); }
+    unsigned char *d_all = nullptr;
+    TRY(dmalloc(&d_all, (size_t)n * sizeof(P2pBlob)));
+    CU(cudaMemcpyAsync(d_all + (size_t)me * sizeof(P2pBlob), &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(d_all + (size_t)me * sizeof(P2pBlob), d_all, sizeof(P2pBlob), kNcclInt8, c->nccl_comm, c->stream));
+    std::vector<P2pBlob> all(n);
+    CU(cudaMemcpyAsync(all.data(), d_all, (size_t)n * sizeof(P2pBlob), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_all);
+
+    int ok = 1;
+    P2pPeers &pp = c->p2p;
+    memset(&pp, 0, sizeof pp);
+    pp.stride = c->xyzd_stride;
+    std::vector<void *> mapped_xyzd(n, nullptr), mapped_type(n, nullptr), mapped_flags(n, nullptr);
+    mapped_xyzd[me] = c->d_xyzd; mapped_type[me] = c->s.type; mapped_flags[me] = c->d_flags;
+    for (int r = 0; r < n; r++) {
+        ok = ok && all[r].ok && all[r].host == mine.host;
+        for (int k = 0; k < 3; k++) ok = ok && all[r].size[k] == mine.size[k];
+    }
+    const int *gs = c->dom.grid_size;
+    for (int k = 0; k < 27 && ok; k++) {
+        if (k == 13 || !c->push_code_used[k]) continue;
+        const int s[3] = {k % 3 - 1, (k / 3) % 3 - 1, k / 9 - 1};
+        int dc[3], r = -1;
+        for (int d = 0; d < 3; d++) dc[d] = ((mine.coord[d] - s[d]) % gs[d] + gs[d]) % gs[d];
+        for (int q = 0; q < n; q++)
+            if (all[q].coord[0] == dc[0] && all[q].coord[1] == dc[1] && all[q].coord[2] == dc[2]) r = q;
+        if (r < 0) { ok = 0; break; }
+        if (!mapped_xyzd[r]) {
+            if (all[r].pid == mine.pid) {          // two sub-boxes of one process: plain peer access
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, c->device, all[r].device);
+                if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0; cudaGetLastError(); }
+                if (!can) { ok = 0; break; }
+                mapped_xyzd[r] = all[r].p_xyzd; mapped_type[r] = all[r].p_type; mapped_flags[r] = all[r].p_flags;
+            } else {
+                void *px = nullptr, *pt = nullptr, *pf = nullptr;
+                if (cudaIpcOpenMemHandle(&px, all[r].h_xyzd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&pt, all[r].h_type, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&pf, all[r].h_flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    for (void *p : {px, pt, pf}) if (p) cudaIpcCloseMemHandle(p);
+                    ok = 0;
+                    break;
+                }
+                c->p2p_opened.push_back(px); c->p2p_opened.push_back(pt); c->p2p_opened.push_back(pf);
+                mapped_xyzd[r] = px; mapped_type[r] = pt; mapped_flags[r] = pf;
+            }
+        }
+        pp.xyzd[k] = (double *)mapped_xyzd[r]; pp.type[k] = (int8_t *)mapped_type[r]; pp.flags[k] = (unsigned long long *)mapped_flags[r];
+        pp.mask |= 1u << k;
+        push_shift(&c->dom, k, pp.shift[k]);
+    }
+    // the handshake is symmetric (my origin for code k is my destination for 26 - k): both must be mapped
+    for (int k = 0; k < 27 && ok; k++)
+        if (((pp.mask >> k) & 1u) && !((pp.mask >> (26 - k)) & 1u)) ok = 0;
+    // every rank takes the same path
+    int *d_ok = nullptr;
+    TRY(dmalloc(&d_ok, 1));
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, kNcclInt32, kNcclMin, c->nccl_comm, c->stream));
+    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_ok);
+    if (!ok) { p2p_release(c); return 0; }
+    c->p2p_active = true;
+    c->p2p_epoch = 0;
+    c->p2p_ready_sent = 0;
+    return 0;
+}
+
+// one ghost exchange, collective over the sub-boxes like the NCCL path:
+//   [ready signal, unless p2p_post_ready sent it ahead] -> push (waits for the destinations' ready, last CTA signals arrive)
+//   -> wait for every origin's arrive
+static int p2p_exchange(misa_b200_ctx *c, bool positions, cudaStream_t st) {
+    const unsigned long long e = ++c->p2p_epoch;
+    if (c->p2p_ready_sent < e) {
+        k_p2p_ready<<<1, 32, 0, st>>>(c->p2p, e);
+        c->p2p_ready_sent = e;
+        c->launches++;
+    }
+    const int nb = (c->n_push + MISA_BLOCK - 1) / MISA_BLOCK;
+    unsigned int *done = reinterpret_cast<unsigned int *>(c->d_flags + P2P_FLAG_WORDS - 1);
+    if (positions) k_p2p_push_x<<<nb, MISA_BLOCK, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
+    else k_p2p_push_df<<<nb, MISA_BLOCK, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
+    k_p2p_wait_arrive<<<1, 32, 0, st>>>(c->p2p, e, c->d_flags, c->d_p2p_err);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+// Called right after the last reader of this sub-box's ghosts in a step (the force kernel of the sync-free step): frees
+// the ghosts for the next `ahead` exchanges, so that the neighbours' next pushes find the flag already there.
+static int p2p_post_ready(misa_b200_ctx *c, int ahead, cudaStream_t st) {
+    if (!(c->p2p_active && c->opt_p2p)) return 0;
+    const unsigned long long e = c->p2p_epoch + (unsigned long long)ahead;
+    if (c->p2p_ready_sent >= e) return 0;
+    k_p2p_ready<<<1, 32, 0, st>>>(c->p2p, e);
+    c->p2p_ready_sent = e;
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}

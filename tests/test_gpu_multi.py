@@ -42,6 +42,7 @@ def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka, opts=""):
     ctx.step(steps)
     np.save(os.path.join(out_dir, "lat%d.npy" % rank), ctx.download())
     np.save(os.path.join(out_dir, "inter%d.npy" % rank), ctx.download_inter())
+    np.save(os.path.join(out_dir, "p2p%d.npy" % rank), np.array([ctx.query("p2p"), ctx.query("p2p_error")]))
     ctx.close()
 
 
@@ -91,6 +92,27 @@ def test_two_gpus_serial_and_overlapped_exchange(tmp_path, opts):
     w = _run(tmp_path, (16, 8, 8), (2, 1, 1), (90, 6, 4), steps=5, opts=opts)
     _compare(tmp_path, w, 1e-12, 1e-9)
     w.close()
+
+
+def test_two_gpus_direct_push_equals_staged_nccl_exchange(tmp_path):
+    """csrc/p2p.cuh (one push kernel into the neighbour's HBM + flag handshakes) against the three staged NCCL
+    exchanges: the ghosts get the same bits, so the whole trajectory is identical in every field."""
+    out = {}
+    for name, opts in (("p2p", ""), ("nccl", "p2p=0")):
+        d = tmp_path / name
+        d.mkdir()
+        w = _run(d, (16, 10, 8), (2, 1, 1), (90, 6, 4), steps=6, opts=opts)
+        _compare(d, w, 1e-12, 1e-9)
+        w.close()
+        out[name] = [np.load(os.path.join(str(d), "lat%d.npy" % r)) for r in range(2)]
+        flags = [np.load(os.path.join(str(d), "p2p%d.npy" % r)) for r in range(2)]
+        assert all(f[1] == 0 for f in flags)
+        if name == "p2p" and flags[0][0] != 1:
+            pytest.skip("no peer access between the two GPUs: the NCCL path ran")
+        assert all(f[0] == (1 if name == "p2p" else 0) for f in flags)
+    for r in range(2):
+        for fld in ("type", "x", "v", "f", "rho", "df"):
+            assert np.array_equal(out["p2p"][r][fld], out["nccl"][r][fld]), (r, fld)
 
 
 def test_two_gpus_pka_migrates_across_sub_boxes(tmp_path):

@@ -131,3 +131,44 @@ def test_sub_box_state_matches_reference_builder_rule():
     assert own["id"][0, 0, 0] == 1 + 8
     loc = synth.create_global_state((4, 8, 8))
     assert np.array_equal(own["v"], loc["v"])
+
+
+@pytest.mark.parametrize("phase,grid", [((12, 12, 12), (2, 2, 2)), ((12, 8, 10), (2, 1, 1)), ((8, 16, 18), (1, 2, 3)), ((8, 9, 10), (1, 1, 1))])
+def test_direct_push_map_equals_the_staged_exchange(phase, grid, pot):
+    """misa_b200_plan_push (what csrc/p2p.cuh applies with one kernel over NVLink peer memory) against the reference's
+    three staged exchanges run by the oracle on every sub-box: same ghost positions (bits) and types everywhere."""
+    w = O.World(phase, grid=grid, a=A, crf=CRF, pot=pot)
+    w.fill_lattice()
+    rs = np.random.RandomState(5)
+    for r in range(w.n_ranks):                        # distinguishable owned values, ghosts poisoned
+        a = w.atoms(r).reshape(w.shape(r))
+        own = w.owned_slices(r)
+        keep_x, keep_t = a["x"][own].copy(), a["type"][own].copy()
+        a["x"][...] = np.nan
+        a["type"][...] = -7
+        a["x"][own] = keep_x + rs.uniform(-0.2, 0.2, keep_x.shape)
+        a["type"][own] = rs.randint(0, 3, keep_t.shape)
+    before = [w.atoms(r).copy() for r in range(w.n_ranks)]
+    w.L.ora_exchange_atom_first(w.h)
+    coord_of = [tuple(w.rank(r).dom.grid_coord) for r in range(w.n_ranks)]
+    rank_at = {c: r for r, c in enumerate(coord_of)}
+    got = [b.copy() for b in before]
+    n_ghost = 0
+    for r in range(w.n_ranks):
+        dom = capi.make_domain(phase, grid, coord_of[r], A, CRF)
+        dst, src, code, shift = capi.plan_push(dom)
+        n_ghost = len(dst)
+        assert len(np.unique(dst)) == len(dst)
+        for k in np.unique(code):
+            s = (k % 3 - 1, (k // 3) % 3 - 1, k // 9 - 1)
+            to = rank_at[tuple((coord_of[r][d] - s[d]) % grid[d] for d in range(3))]
+            m = code == k
+            got[to]["x"][dst[m]] = before[r]["x"][src[m]] + shift[k]
+            got[to]["type"][dst[m]] = before[r]["type"][src[m]]
+    e = w.shape(0)
+    assert n_ghost == e[0] * e[1] * e[2] - 2 * (phase[0] // grid[0]) * (phase[1] // grid[1]) * (phase[2] // grid[2])
+    for r in range(w.n_ranks):
+        ref = w.atoms(r)
+        assert np.array_equal(got[r]["type"], ref["type"])
+        assert np.array_equal(got[r]["x"].view(np.uint64), ref["x"].view(np.uint64))   # incl. the image shifts, bit for bit
+    w.close()

@@ -1,0 +1,5 @@
+set -x
+nvidia-smi topo -m > gpurun_out/r01aa_topo.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -40 > gpurun_out/r01aa_pytest_multi.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 > gpurun_out/r01aa_bench_n2.json 2> gpurun_out/r01aa_bench_n2.err
+MISA_B200_OPTS=p2p=0 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --warmup 10 > gpurun_out/r01aa_bench_n2_nccl.json 2> gpurun_out/r01aa_bench_n2_nccl.err
