@@ -372,9 +372,10 @@ def run_b200(args):
         ctx.step_host(host, 1)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": n_gpus * atoms_per_gpu * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ctx.n_ext * 104,
-           "d2h_bytes_per_step": ctx.n_ext * 104, "steps": e2e_steps,
-           "api": "misa_b200_step_host(ctx, AtomElement* host, 1): upload AoS, one step, download AoS"}
+    e2e = {"value": n_gpus * atoms_per_gpu * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ctx.n_owned * 104,
+           "d2h_bytes_per_step": ctx.n_owned * 104, "steps": e2e_steps,
+           "api": "misa_b200_step_host(ctx, AtomElement* host, 1): upload the owned box of the host AoS array (pitched 3-D copy "
+                  "from page-locked memory), one step, download the owned box"}
     # the three reference hooks on the host array (EAM part of a step only; what the unmodified driver calls)
     t0 = time.perf_counter()
     for _ in range(3):

@@ -355,9 +355,17 @@ k_ghost_fill_1(const int n, const int *__restrict__ dst, const int *__restrict__
 enum { F_ID = 1, F_TYPE = 2, F_X = 4, F_V = 8, F_F = 16, F_RHO = 32, F_DF = 64, F_ALL = 127 };
 
 __global__ void __launch_bounds__(MISA_BLOCK)
-k_aos_to_soa(const long long n_ext, const long long H, const unsigned long long *__restrict__ aos, const Soa s, const int fields) {
+k_aos_to_soa(const long long n_ext, const long long H, const unsigned long long *__restrict__ aos, const Soa s, const int fields,
+             const Geo g = Geo(), const int owned_only = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_ext) return;
+    if (owned_only) {
+        const int sx = 2 * g.sxc;
+        const int x = (int)(idx % sx);
+        const long long r = idx / sx;
+        const int y = (int)(r % g.sy), z = (int)(r / g.sy);
+        if (x < 2 * g.gx || x >= 2 * (g.gx + g.nx) || y < g.gy || y >= g.gy + g.ny || z < g.gz || z >= g.gz + g.nz) return;
+    }
     const long long d = ref_to_dev(idx, H);
     const unsigned long long *w = aos + idx * AOS_WORDS;
     if (fields & F_ID) s.id[d] = w[0];

@@ -693,16 +693,33 @@ static int ensure_aos(misa_b200_ctx *c) {
     if (!c->d_aos) TRY(dmalloc(&c->d_aos, (size_t)c->geo.n_ext * 104));
     return 0;
 }
-static int h2d_aos(misa_b200_ctx *c, const void *atoms, int fields) {
+// the owned box of a ghost-extended AoS array as one pitched 3-D copy: rows of 2*nx records (20.8 KB at 100 cells)
+static int copy_owned_box(misa_b200_ctx *c, void *dst, const void *src, cudaMemcpyKind kind) {
+    const Geo &g = c->geo;
+    const size_t rec = 104, pitch = 2 * (size_t)g.sxc * rec;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), pitch, pitch, (size_t)g.sy);
+    p.dstPtr = make_cudaPitchedPtr(dst, pitch, pitch, (size_t)g.sy);
+    p.srcPos = p.dstPos = make_cudaPos(2 * (size_t)g.gx * rec, (size_t)g.gy, (size_t)g.gz);
+    p.extent = make_cudaExtent(2 * (size_t)g.nx * rec, (size_t)g.ny, (size_t)g.nz);
+    p.kind = kind;
+    CU(cudaMemcpy3DAsync(&p, c->stream));
+    return 0;
+}
+static int h2d_aos(misa_b200_ctx *c, const void *atoms, int fields, int owned_only = 0) {
     TRY(ensure_aos(c));
     c->minor_valid = false; // the host may have put any species anywhere
-    CU(cudaMemcpyAsync(c->d_aos, atoms, (size_t)c->geo.n_ext * 104, cudaMemcpyHostToDevice, c->stream));
+    if (owned_only) TRY(copy_owned_box(c, c->d_aos, atoms, cudaMemcpyHostToDevice));
+    else CU(cudaMemcpyAsync(c->d_aos, atoms, (size_t)c->geo.n_ext * 104, cudaMemcpyHostToDevice, c->stream));
     Slot sl(c, MISA_B200_K_XFER);
-    k_aos_to_soa<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->geo.H, (const unsigned long long *)c->d_aos, c->s, fields);
+    k_aos_to_soa<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->geo.H, (const unsigned long long *)c->d_aos, c->s, fields, c->geo, owned_only);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
 }
+// owned_only: 1 = convert only owned records but copy the whole array back (compat hooks: the host's ghost records pass
+// through the staging copy untouched); 2 = also copy only the owned box (the host's ghost records are not written at all)
 static int d2h_aos(misa_b200_ctx *c, void *atoms, int fields, int owned_only) {
     TRY(ensure_aos(c));
     {
@@ -711,7 +728,8 @@ static int d2h_aos(misa_b200_ctx *c, void *atoms, int fields, int owned_only) {
         c->launches++;
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(atoms, c->d_aos, (size_t)c->geo.n_ext * 104, cudaMemcpyDeviceToHost, c->stream));
+    if (owned_only == 2) TRY(copy_owned_box(c, atoms, c->d_aos, cudaMemcpyDeviceToHost));
+    else CU(cudaMemcpyAsync(atoms, c->d_aos, (size_t)c->geo.n_ext * 104, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1604,17 +1622,22 @@ extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
     return 0;
 }
 
-// Host-buffer form of the step loop: the AoS array the reference driver owns goes in, n steps run on the
-// device, and the array comes back coherent (every field of every site), so the unmodified host code around
-// the loop (dump, thermo, stage machine -- reference frontend/md_simulation.cpp:40-121) sees current data.
+// Host-buffer form of the step loop: the AoS array the reference driver owns goes in, n steps run on the device and
+// the OWNED records come back (every field), so the unmodified host code around the loop (dump, thermo, stage machine
+// -- reference frontend/md_simulation.cpp:40-121, all of which read owned sites only) sees current data. Ghost records
+// carry no information across a step in the reference either: x / type / df are refilled by exchangeAtom and the df
+// halo before they are read, rho / f are cleared (src/atom.cpp:86-146) -- so after the first call (full upload: the
+// species census covers the ghost shell) only the owned box crosses PCIe, as one pitched 3-D copy each way, and the
+// host's ghost records are left as they were.
 extern "C" int misa_b200_step_host(misa_b200_ctx *c, void *atoms, int n_steps) {
     REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_step_host: null argument");
     REQ(c->have_off && c->have_pot, MISA_B200_ESTATE, "misa_b200_step_host: offsets / potential not set");
-    TRY(h2d_aos(c, atoms, F_ALL));
+    const bool first = !c->census_valid || !c->have_atoms;
+    TRY(h2d_aos(c, atoms, F_ALL, first ? 0 : 1));
     if (!c->census_valid) { TRY(census_local(c)); TRY(census_fetch(c)); }
     c->have_atoms = true;
     TRY(misa_b200_step(c, n_steps));
-    return d2h_aos(c, atoms, F_ALL, 0);
+    return d2h_aos(c, atoms, F_ALL, first ? 0 : 2);
 }
 
 extern "C" int misa_b200_timed_steps(misa_b200_ctx *c, int n_steps, double *ms) {

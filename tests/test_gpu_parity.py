@@ -350,3 +350,32 @@ def test_fused_half_kicks_are_bit_identical():
     for other in out[1:]:
         for fld in ("x", "v", "f", "rho", "df"):
             assert np.array_equal(out[0][fld], other[fld]), fld
+
+
+def test_step_host_moves_only_the_owned_box_and_equals_resident_steps():
+    """misa_b200_step_host after its first call uploads / downloads the owned records only (one pitched 3-D copy each
+    way): same trajectory, bit for bit, as resident stepping; ghost records of the host array are left alone."""
+    st = cm.make_state((9, 8, 10), sigma=0.04)
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    ctx.step(4)
+    want = cm.owned(ctx, ctx.download()).copy()
+    ctx.close()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    host = ctx.download()
+    ctx.host_register(host)
+    ctx.step_host(host, 1)                      # resident state exists: already the owned-box path
+    ghost = np.ones(ctx.ext_shape, dtype=bool)
+    ghost[ctx.owned] = False
+    h3 = host.reshape(ctx.ext_shape)
+    h3["x"][ghost] = 12345.0                    # poison: must neither be read nor overwritten
+    h3["rho"][ghost] = -1.0
+    for _ in range(3):
+        ctx.step_host(host, 1)
+    got = cm.owned(ctx, host)
+    for fld in ("type", "id", "x", "v", "f", "rho", "df"):
+        assert np.array_equal(got[fld], want[fld]), fld
+    assert np.all(h3["x"][ghost] == 12345.0) and np.all(h3["rho"][ghost] == -1.0)
+    ctx.host_unregister(host)
+    ctx.close()
