@@ -44,6 +44,7 @@ struct Soa {
     int8_t *type;
     unsigned long long *id;
     unsigned char *ulev;   // ceil(|x - site| / 0.01a) of the valid atom on the site (k_verlet1 / k_max_displacement): per-warp stencil pruning
+    unsigned char *hot;    // [H] per CELL: an atom displaced by more than the marking level sits within reach, or a ghost may (k_verlet1)
 };
 
 struct InterSoa {  // off-lattice atoms: [0, n_local) local, [cap/2, cap/2 + n_ghost) ghost copies
@@ -88,6 +89,11 @@ struct misa_b200_ctx {
     static const int kLevels = 21;
     static const int kPairLevels = 41;    // prefix lengths of the distance-sorted full list: sites closer than (crf + 0.01 L) a
     int prefix_n[kPairLevels] = {0};
+    // partner bound of the per-warp pruning: atoms above level mark_T mark the cells within reach in k_verlet1; warps that see no
+    // mark bound their partners by mark_T instead of the global maximum (eam_smem.cuh:list_len)
+    unsigned char *d_hot = nullptr, *d_hot_init = nullptr;
+    int opt_mark = 1, mark_T_next = 0, mark_T_used = 0, mark_epoch = 0;   // d_hot: epoch bytes; d_hot_init: static edge map
+    bool mark_valid = false;
     int level_n[kLevels] = {0};
     int level_near[kLevels] = {0};        // leading entries (lists are sorted by site distance) that are almost surely in range
     int near_full = 0;

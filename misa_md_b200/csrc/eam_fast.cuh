@@ -251,6 +251,7 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
     const int lg = base_level(ls);
+    const bool hot_ok = hot_map_usable(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
@@ -275,7 +276,8 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
         const int ti = s.type[d];
         const int *off = s_off + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0));
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
+                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double acc = 0.0;
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
@@ -364,6 +366,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
     const int lg = base_level(ls);
+    const bool hot_ok = hot_map_usable(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
@@ -390,7 +393,8 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         const int ti = s.type[d];
         const int tic = max(ti, 0);
         const int *off = s_off + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0));
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
+                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         unsigned long long d_eli = 0;
         if (!SINGLE && EAM_MULTI_GENERIC) d_eli = dir[tic];

@@ -188,6 +188,13 @@ struct LevelSel {
     const unsigned char *ulev;
     int prefix[EAM_PAIR_LEVELS];
     int host_level;                         // lg when dmax2_bits is null; -1: no pruning (full list)
+    // cheaper partner bound: k_verlet1 marks (with the step's epoch byte) the cells within reach of every atom above level
+    // hot_T; `edge` marks the cells whose partners may be ghosts (their levels are not kept). A warp that sees neither
+    // bounds its partners by hot_T instead of lg
+    const unsigned char *hot, *edge;
+    const unsigned long long *hot_count;    // atoms that marked (or wanted to) this step; above MARK_CAP the map is incomplete
+    int hot_T, hot_epoch;
+    long long H;
 };
 __device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs, int &n_off, int &n_near) {
     if (!ls.dmax2_bits) return;
@@ -203,8 +210,10 @@ __device__ __forceinline__ int base_level(const LevelSel &ls) {
     return (int)min(ceil(d / ls.step), 1000.0);
 }
 // offsets a warp loops: lw = largest displacement level among its own atoms (warp-uniform)
-__device__ __forceinline__ int list_len(const LevelSel &ls, const int lg, const int lw) {
-    const int L = lg + lw;
+__device__ __forceinline__ bool hot_map_usable(const LevelSel &ls) { return ls.hot && *ls.hot_count <= MARK_CAP; }
+__device__ __forceinline__ bool cell_hot(const LevelSel &ls, const long long cell) { return ls.hot[cell] == ls.hot_epoch || ls.edge[cell] != 0; }
+__device__ __forceinline__ int list_len(const LevelSel &ls, const int lg, const int lw, const bool hot) {
+    const int L = lw + (hot ? lg : min(lg, ls.hot_T));
     return (lg >= 0 && L < EAM_PAIR_LEVELS) ? ls.prefix[L] : ls.n_full;
 }
 

@@ -111,6 +111,7 @@ k_rho_a(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
     const int lg = base_level(ls);
+    const bool hot_ok = hot_map_usable(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list);
@@ -135,7 +136,8 @@ k_rho_a(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         int ti = 0;
         if (NEEDTYPE) ti = s.type[d];
         const int *off = s_off + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0));
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
+                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double *__restrict__ prow = sy.pair + pair_index(d, 0, n_half);
         double acc = 0.0;
@@ -257,6 +259,7 @@ k_force_a(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
     const int lg = base_level(ls);
+    const bool hot_ok = hot_map_usable(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list);
@@ -283,7 +286,8 @@ k_force_a(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         int ti = maj;
         if (NEEDTYPE || DILUTE) ti = s.type[d];
         const int *off = s_off + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0));
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
+                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         double *__restrict__ prow = sy.pair + pair_index(d, 0, n_half);
         double fx = 0.0, fy = 0.0, fz = 0.0;

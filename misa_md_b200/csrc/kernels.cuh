@@ -179,7 +179,8 @@ k_force(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ of
 //      with explicit round-to-nearest mul/add (no FMA contraction) so x, v and the run-away decision are
 //      bit-exact. Run-aways are appended to `runaway_sites` (device indices); the site is vacated by
 //      k_decide_vacate after the list has been sorted into the reference's k,j,i order. ------------------
-struct VerletPar { double dt; double c[MISA_MAX_TYPES]; };
+#define MARK_CAP 4096     // marking atoms per step; beyond it the map is void (stepinfo[2] tells the stencil kernels)
+struct VerletPar { double dt; double c[MISA_MAX_TYPES]; int mark_T; unsigned char *hot; unsigned char epoch; unsigned long long *mark_count; };
 // max over the warp, then one atomicMax on the bit pattern (non-negative doubles order like unsigned integers)
 __device__ __forceinline__ void report_max(double v, unsigned long long *__restrict__ out) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -231,7 +232,17 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
         if (slot < runaway_cap) runaway_sites[slot] = d;
         else atomicExch(&counters[3], 1);
     }
-    s.ulev[d] = disp_level(dist, g.a);
+    const int lev = disp_level(dist, g.a);
+    s.ulev[d] = (unsigned char)lev;
+    if (vp.hot && lev > vp.mark_T && atomicAdd(vp.mark_count, 1ULL) < MARK_CAP) {
+        // a far-displaced atom (a few dozen of 2 M at 300 K): every cell within the stencil reach learns that the cheap
+        // partner bound mark_T does not hold around it. The mark is the step's epoch byte, so the map is never cleared: a
+        // stale byte that aliases 255 steps later only makes a warp keep the global bound (the safe side).
+        const long long cell = ((long long)(z + g.gz) * g.sy + (y + g.gy)) * g.sxc + (cx + g.gx);
+        for (int dz = -g.gz; dz <= g.gz; dz++)
+            for (int dy = -g.gy; dy <= g.gy; dy++)
+                for (int dx = -g.gx; dx <= g.gx; dx++) vp.hot[cell + ((long long)dz * g.sy + dy) * g.sxc + dx] = vp.epoch;
+    }
     return dist;
 }
 

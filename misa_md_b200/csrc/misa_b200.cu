@@ -253,6 +253,17 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.v[k], n)); TRY(dmalloc(&c->s.f[k], n)); }
     TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n)); TRY(dmalloc(&c->s.ulev, n));
     CU(cudaMemset(c->s.ulev, 0xff, n));
+    {   // hot-cell map (ctx.h): the template marks every cell whose stencil reaches into the ghost shell (ghost levels are not kept)
+        const Geo &g = c->geo;
+        std::vector<unsigned char> tmpl((size_t)g.H, 1);
+        for (int z = 2 * g.gz; z < g.sz - 2 * g.gz; z++)
+            for (int y = 2 * g.gy; y < g.sy - 2 * g.gy; y++)
+                for (int x = 2 * g.gx; x < g.sxc - 2 * g.gx; x++) tmpl[((size_t)z * g.sy + y) * g.sxc + x] = 0;
+        TRY(dmalloc(&c->d_hot, (size_t)g.H)); TRY(dmalloc(&c->d_hot_init, (size_t)g.H));
+        CU(cudaMemcpy(c->d_hot_init, tmpl.data(), (size_t)g.H, cudaMemcpyHostToDevice));
+        CU(cudaMemset(c->d_hot, 0, (size_t)g.H));
+        c->s.hot = c->d_hot;
+    }
     for (int k = 0; k < 3; k++) { CU(cudaMemset(c->s.v[k], 0, n * 8)); CU(cudaMemset(c->s.f[k], 0, n * 8)); }
     CU(cudaMemset(c->s.rho, 0, n * 8)); CU(cudaMemset(c->s.type, 0xff, n)); CU(cudaMemset(c->s.id, 0, n * 8));
     {
@@ -362,7 +373,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     if (c->tex_all) cudaDestroyTextureObject(c->tex_all);
     cudaFree(c->d_xyzd);
     for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
-    cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id); cudaFree(c->s.ulev);
+    cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id); cudaFree(c->s.ulev); cudaFree(c->d_hot); cudaFree(c->d_hot_init);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -793,6 +804,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "dilute")) c->opt_dilute = value;
     else if (!strcmp(name, "sym")) c->opt_sym = value;
     else if (!strcmp(name, "p2p")) c->opt_p2p = value;
+    else if (!strcmp(name, "mark")) c->opt_mark = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
@@ -823,6 +835,13 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
     else if (!strcmp(name, "n_minor")) *value = c->minor_valid ? c->n_minor : -1;
     else if (!strcmp(name, "n_half")) *value = c->n_half;
     else if (!strcmp(name, "p2p")) *value = c->p2p_active && c->opt_p2p ? 1 : 0;
+    else if (!strcmp(name, "mark_count")) {   // diagnostic: atoms that marked in the last k_verlet1
+        unsigned long long n = 0;
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(&n, c->d_stepinfo + 2, sizeof n, cudaMemcpyDeviceToHost));
+        *value = (double)n;
+    }
+    else if (!strcmp(name, "mark_level")) *value = c->mark_valid ? c->mark_T_used : -1;
     else if (!strcmp(name, "p2p_error")) *value = c->h_p2p_err ? (double)*c->h_p2p_err : 0.0;
     else if (!strcmp(name, "sym")) *value = planned && sym_active(c, sp) ? 1 : 0;
     else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
@@ -938,6 +957,7 @@ static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off, int 
 
 // measure dmax over the whole ghost-extended array (positions as they are now, ghosts included)
 static int measure_displacement(misa_b200_ctx *c) {
+    c->mark_valid = false;   // levels are re-measured for every site, nothing is marked
     CU(cudaMemsetAsync(c->d_stepinfo + 1, 0, sizeof(unsigned long long), c->stream));
     k_max_displacement<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo, c->s, c->d_stepinfo + 1);
     c->launches++;
@@ -946,6 +966,7 @@ static int measure_displacement(misa_b200_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     memcpy(&c->dmax2, c->h_stepinfo + 1, sizeof(double));
     c->dmax_valid = true;
+    c->mark_T_next = std::max(0, (int)std::min(ceil((sqrt(c->dmax2) + 1e-6) / (0.01 * c->geo.a)), 1000.0) - 3);
     return 0;
 }
 
@@ -1100,6 +1121,8 @@ static LevelSel make_levelsel(const misa_b200_ctx *c, const unsigned long long *
     ls.step = 0.01 * c->geo.a;
     ls.ulev = c->s.ulev;
     for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) ls.prefix[L] = c->prefix_n[L];
+    ls.H = c->geo.H;
+    if (c->mark_valid && c->opt_mark) { ls.hot = c->d_hot; ls.edge = c->d_hot_init; ls.hot_T = c->mark_T_used; ls.hot_epoch = c->mark_epoch; ls.hot_count = c->d_stepinfo + 2; }
     if (!c->opt_prune) return ls;
     if (!dmax2) {   // the host's knowledge (serial path): same rounding as pick_list
         if (c->dmax_valid) ls.host_level = (int)std::min(ceil((sqrt(c->dmax2) + 1e-6) / ls.step), 1000.0);
@@ -1390,6 +1413,7 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
     VerletPar vp;
     vp.dt = c->dt;
     for (int i = 0; i < MISA_MAX_TYPES; i++) vp.c[i] = c->dt_inv_m[i];
+    vp.mark_T = 0; vp.hot = nullptr; vp.epoch = 0; vp.mark_count = nullptr;
     return vp;
 }
 
@@ -1420,10 +1444,17 @@ static int update_activity(misa_b200_ctx *c) {
 static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
-    const VerletPar vp = verlet_par(c);
+    VerletPar vp = verlet_par(c);
     Slot sl(c, MISA_B200_K_VERLET1);
+    c->mark_valid = false;
+    if (c->opt_mark && c->opt_prune) {   // this step's marks carry a fresh epoch byte (1..255): nothing to clear
+        c->mark_epoch = c->mark_epoch % 255 + 1;
+        c->mark_T_used = c->mark_T_next;
+        vp.mark_T = c->mark_T_used; vp.hot = c->d_hot; vp.epoch = (unsigned char)c->mark_epoch; vp.mark_count = c->d_stepinfo + 2;
+        c->mark_valid = true;
+    }
     CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
-    CU(cudaMemsetAsync(c->d_stepinfo, 0, 2 * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->d_stepinfo, 0, 3 * sizeof(unsigned long long), c->stream));   // [2]: atoms that marked (kernels.cuh MARK_CAP)
     if (kick2) k_verlet1<true><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
     else k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
     c->launches++;
@@ -1440,6 +1471,8 @@ static int verlet1_finish(misa_b200_ctx *c) {
     // re-occupy vacancies far from the site) it is re-measured after the ghost exchange instead.
     memcpy(&c->dmax2, c->h_stepinfo + 1, sizeof(double));
     c->dmax_valid = !c->inter_active;
+    // marking level of the NEXT step: three levels under the current global maximum -- a few dozen atoms of millions lie above
+    c->mark_T_next = std::max(0, (int)std::min(ceil((sqrt(c->dmax2) + 1e-6) / (0.01 * c->geo.a)), 1000.0) - 3);
     if (c->inter_active) {
         Slot sl(c, MISA_B200_K_INTER);
         TRY(inter_decide(c, c->last_runaways));

@@ -379,3 +379,45 @@ def test_step_host_moves_only_the_owned_box_and_equals_resident_steps():
     assert np.all(h3["x"][ghost] == 12345.0) and np.all(h3["rho"][ghost] == -1.0)
     ctx.host_unregister(host)
     ctx.close()
+
+
+def test_hot_cell_marks_bound_the_partner_rigorously():
+    """Per-warp stencil prefixes bound the partner atom by the marking level T unless an atom above T sits within reach
+    (k_verlet1 marks those cells). One atom 0.19a off its site, a partner in its <311>/2 shell (2.18a) 0.04a towards it:
+    the pair is in range (1.949a < crf) although partner level + T says it cannot be -- only the mark keeps it. Also:
+    marks on / off give identical bits on a thermal state."""
+    st = cm.make_state((14, 14, 14), t_set=1e-6)
+    x = st["x"]
+    a_site, c_site = (7, 7, 14), (7, 8, 17)             # corner of cell (7,7,7); centre of cell (8,8,7): separation (1.5,1.5,0.5)a
+    u = x[c_site] - x[a_site]
+    assert abs(np.linalg.norm(u) / cm.A - 2.179) < 1e-3
+    u /= np.linalg.norm(u)
+    x[a_site] += 0.19 * cm.A * u
+    x[c_site] -= 0.04 * cm.A * u
+    w = cm.oracle_world(st)
+    w.prepare()
+    w.step()
+    ctx = cm.gpu_context(st)
+    ctx.prepare()
+    ctx.step(1)
+    assert 0 <= ctx.query("mark_level") < 19 and 1 <= ctx.query("mark_count") <= 4
+    got, ref = cm.owned(ctx, ctx.download()), cm.owned(ctx, w.atoms(0))
+    for fld in ("rho", "df", "f"):
+        assert cm.rel_err(got[fld], ref[fld]) < TOL, fld
+    # the pair matters at the tolerance: without it rho of the partner is off by far more than 1e-10
+    r = np.linalg.norm(st["x"][c_site] - st["x"][a_site])
+    assert r < cm.A * cm.CRF
+    ctx.close()
+    w.close()
+    st = cm.make_state((12, 13, 14), sigma=0.05)
+    out = []
+    for mark in (1, 0):
+        ctx = cm.gpu_context(st)
+        ctx.set_option("mark", mark)
+        ctx.prepare()
+        ctx.step(5)
+        assert (ctx.query("mark_level") >= 0) == bool(mark)
+        out.append(cm.owned(ctx, ctx.download()).copy())
+        ctx.close()
+    for fld in ("x", "v", "f", "rho", "df"):
+        assert np.array_equal(out[0][fld], out[1][fld]), fld
