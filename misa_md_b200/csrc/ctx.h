@@ -128,6 +128,8 @@ struct misa_b200_ctx {
     unsigned char *d_mcount = nullptr, *d_mentry = nullptr;
     int *d_minor = nullptr, *d_minor_count = nullptr; // device indices of the owned minority-species atoms
     int n_minor = 0, minor_maj = 0;
+    int opt_minor_staged = 0;             // minority atoms: per-species launch with that species' tables in shared memory -- measured SLOWER
+                                          // (force 0.987 vs 0.944 ms at 97:2:1: two launches x 154 KB of staging per CTA, 70 KB of L1 left), off
     bool minor_valid = false;
     int opt_smem = 1;                     // use the shared-memory table kernels when possible
     // pair-symmetric stencil passes (eam_sym.cuh): the leading n_half entries of every offset list are the "upper"

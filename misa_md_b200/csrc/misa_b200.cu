@@ -113,6 +113,7 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_rho_f<true, true, true, false, true>)); OPTIN((k_rho_f<true, true, false, false, true>));
     OPTIN((k_rho_f<true, false, true, false, true>)); OPTIN((k_rho_f<true, false, false, false, true>));
     OPTIN((k_force_f<true, true, false, true>)); OPTIN((k_force_f<true, false, false, true>));
+    OPTIN(k_force_minor_s);
     OPTIN((k_rho_a<true, false>)); OPTIN((k_rho_a<false, false>)); OPTIN((k_rho_a<true, true>)); OPTIN((k_rho_a<false, true>));
     OPTIN((k_force_a<true, false>)); OPTIN((k_force_a<false, false>)); OPTIN((k_force_a<true, true>)); OPTIN((k_force_a<false, true>));
 #undef OPTIN
@@ -805,6 +806,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "sym")) c->opt_sym = value;
     else if (!strcmp(name, "p2p")) c->opt_p2p = value;
     else if (!strcmp(name, "mark")) c->opt_mark = value;
+    else if (!strcmp(name, "minor_staged")) c->opt_minor_staged = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
@@ -1281,6 +1283,32 @@ static int launch_df(misa_b200_ctx *c) {
     CU(cudaGetLastError());
     return 0;
 }
+// atoms of the minority species of a dilute alloy: one launch per species with its tables staged (k_force_minor_s), or the
+// global-table kernel when the three tables do not fit
+static int launch_force_minor(misa_b200_ctx *c, const StagePlan &sp, const int *offs, int n_off, const LevelSel &ls, const TexAll &tex) {
+    if (c->n_minor <= 0) return 0;
+    const Geo &g = c->geo;
+    const int nt = c->tab.n_types, maj = sp.staged_id[0];
+    const size_t sb3 = (size_t)sp.off_bytes + (size_t)3 * sp.rows_s * 16;
+    if (c->opt_minor_staged && sb3 + 1024 <= (size_t)c->smem_optin) {
+        for (int t = 0; t < nt; t++) {
+            if (t == maj || c->census[t] == 0) continue;
+            StagePlan s3 = sp;
+            s3.n_staged = 3;
+            s3.staged_id[0] = maj; s3.staged_id[1] = t; s3.staged_id[2] = MISA_MAX_TYPES + t * nt + maj;
+            const int grid = std::max(1, std::min(c->sm_count, (c->n_minor + EAM_THREADS / 32 - 1) / (EAM_THREADS / 32)));
+            k_force_minor_s<<<grid, EAM_THREADS, sb3, c->stream>>>(g, c->s, c->tab, s3, offs, n_off, ls, c->d_minor, c->n_minor, tex, t);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        return 0;
+    }
+    const int mgrid = std::min((c->n_minor + 7) / 8, std::max(1, c->sm_count) * 8);
+    k_force_minor<<<mgrid, 256, 0, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, ls, c->d_minor, c->n_minor, tex);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
 static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = StencilOpt()) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
@@ -1313,12 +1341,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
 #undef FORCE_B
         c->launches += 2;
         CU(cudaGetLastError());
-        if (dil && c->n_minor > 0) {
-            const int mgrid = std::min((c->n_minor + 7) / 8, std::max(1, c->sm_count) * 8);
-            k_force_minor<<<mgrid, 256, 0, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, ls, c->d_minor, c->n_minor, tex);
-            c->launches++;
-            CU(cudaGetLastError());
-        }
+        if (dil) TRY(launch_force_minor(c, sp, offs, n_off, ls, tex));
         return 0;
     }
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
@@ -1335,12 +1358,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         }
         // atoms of a minority species: ALL of them with the launch that runs after the df halo has arrived (the whole-box
         // launch or the boundary one), one warp per atom
-        if (so.region != 1 && c->n_minor > 0) {
-            const int mgrid = std::min((c->n_minor + 7) / 8, std::max(1, c->sm_count) * 8);
-            k_force_minor<<<mgrid, 256, 0, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, ls, c->d_minor, c->n_minor, tex);
-            c->launches++;
-            CU(cudaGetLastError());
-        }
+        if (so.region != 1) TRY(launch_force_minor(c, sp, offs, n_off, ls, tex));
         return 0;
     }
     // non-dilute alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the
@@ -1580,9 +1598,20 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
     interior.region = 1; interior.dmax2 = c->d_stepinfo + 1; interior.reserve_sms = c->opt_reserve;
     boundary.region = 2; boundary.dmax2 = c->d_stepinfo_g + 1;
     if (!overlap) {
-        TRY(activity_enqueue(c, c->stream));
-        CU(cudaEventRecord(c->ev_act, c->stream));
-        TRY(halo_forward(c, true));
+        if (p2p && c->stream2) {
+            // the all-reduce of the activity / displacement words (NCCL, latency-bound) runs beside the position push, which
+            // does not touch the communicator; rho needs both (it reads the global maximum)
+            CU(cudaEventRecord(c->ev_v1, c->stream));
+            CU(cudaStreamWaitEvent(c->stream2, c->ev_v1, 0));
+            TRY(activity_enqueue(c, c->stream2));
+            CU(cudaEventRecord(c->ev_act, c->stream2));
+            TRY(halo_forward(c, true));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_act, 0));
+        } else {
+            TRY(activity_enqueue(c, c->stream));
+            CU(cudaEventRecord(c->ev_act, c->stream));
+            TRY(halo_forward(c, true));
+        }
         TRY(launch_rho(c, true, false, whole));
         TRY(halo_forward(c, false));
         TRY(launch_force(c, false, whole));
