@@ -350,16 +350,18 @@ def run_b200(args):
         elif cnt:
             kernels[name] = {"ms": tot_ms / cnt}
     dom = max((k for k in kernels if "gbs" in kernels[k]), key=lambda k: kernels[k]["ms"])
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch from the committed ncu --set full capture
+    traffic, ncu_pipes = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch + pipe utilisation from the committed ncu --set full capture
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+        traffic, ncu_pipes = tj.get(dom), tj.get(dom + "_pipes")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_atom": BYTES_PER_ATOM[dom], "atoms_per_launch": atoms_per_gpu,
                 "note": "rho/force are fp64-pipe/LSU bound, not HBM bound (DESIGN.md section 4); whole-step "
-                        "HBM fraction in step_hbm_frac"}
+                        "HBM fraction in step_hbm_frac; ncu_pipes = what does bound the kernel (committed capture, % of peak)",
+                "ncu_pipes": ncu_pipes}
     step_gbs = STEP_BYTES_PER_ATOM * atoms_per_gpu * args.steps / (ms * 1e-3) / 1e9
 
     # ---- e2e: host AoS buffers through the C ABI, H2D + D2H inside the timed region --------------------
