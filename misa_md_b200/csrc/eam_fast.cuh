@@ -24,10 +24,10 @@
 #pragma once
 #include "eam_smem.cuh"
 #ifndef EAM_UNROLL_NEAR
-#define EAM_UNROLL_NEAR 2
+#define EAM_UNROLL_NEAR 4
 #endif
 #ifndef EAM_UNROLL_FAR
-#define EAM_UNROLL_FAR 2
+#define EAM_UNROLL_FAR 4
 #endif
 #define EAM_PRAGMA(x) _Pragma(#x)
 #define EAM_UNROLL(n) EAM_PRAGMA(unroll n)

@@ -21,8 +21,11 @@
 #include "ctx.h"
 #include "kernels.cuh"
 
+// Threads per persistent CTA (one CTA per SM). 768 threads leave 85 registers per thread -- room for four neighbour pairs in
+// flight (EAM_UNROLL_NEAR 4 in eam_fast.cuh) -- and measured best on B200 (profiles/r01ai_variants.log: 1024 x unroll 2
+// 1.149 ms/step, 1024 x 4 1.122, 768 x 4 1.106, 640 x 4 1.152, 512 x 4 1.197).
 #ifndef EAM_THREADS
-#define EAM_THREADS 1024
+#define EAM_THREADS 768
 #endif
 #define EAM_MAX_STAGED 4
 
