@@ -385,6 +385,8 @@ def run_b200(args):
     hooks_s = max_over_ranks((time.perf_counter() - t0) / 3)
     e2e["hooks_eam_only_atom_passes_per_s"] = n_gpus * atoms_per_gpu / hooks_s
 
+    if ctx.query("p2p_error"):
+        raise RuntimeError("ghost push over peer memory timed out (p2p_error %d): numbers invalid" % ctx.query("p2p_error"))
     th = ctx.thermo()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -169,9 +169,9 @@ __device__ __forceinline__ int region_unit_to_dev(const Geo &g, const RegionList
     const Region &r = rl.r[b];
     const long long c = (u - r.u0) * 32 + lane;
     if (c >= (long long)r.nx * r.ny * r.nz) return -1;
-    const int cx = (int)(c % r.nx);
-    const long long t = c / r.nx;
-    const int y = (int)(t % r.ny), z = (int)(t / r.ny);
+    const unsigned cu = (unsigned)c, t = cu / (unsigned)r.nx;
+    const int cx = (int)(cu - t * (unsigned)r.nx);
+    const int z = (int)(t / (unsigned)r.ny), y = (int)(t - (unsigned)z * (unsigned)r.ny);
     return (int)(p * g.H + ((long long)(z + r.z0 + g.gz) * g.sy + (y + r.y0 + g.gy)) * g.sxc + (cx + r.x0 + g.gx));
 }
 

@@ -8,10 +8,12 @@
 // ---- index helpers ------------------------------------------------------------------------------
 // owned-cell ordinal c in [0, nx*ny*nz) of sub-lattice p -> device index
 __device__ __forceinline__ int owned_cell_to_dev(const Geo &g, int p, long long c, int &cx, int &y, int &z) {
-    cx = (int)(c % g.nx);
-    const long long r = c / g.nx;
-    y = (int)(r % g.ny);
-    z = (int)(r / g.ny);
+    // device indices are 32-bit throughout (n_ext < 2^31, checked at create): 32-bit divisions, not 64-bit ones
+    const unsigned cu = (unsigned)c, nx = (unsigned)g.nx, ny = (unsigned)g.ny;
+    const unsigned r = cu / nx;
+    cx = (int)(cu - r * nx);
+    z = (int)(r / ny);
+    y = (int)(r - (unsigned)z * ny);
     return (int)(p * g.H + ((long long)(z + g.gz) * g.sy + (y + g.gy)) * g.sxc + (cx + g.gx));
 }
 __host__ __device__ __forceinline__ long long ref_to_dev(long long idx, long long H) { return (idx >> 1) + (idx & 1) * H; }
@@ -192,7 +194,8 @@ __device__ __forceinline__ void report_max(double v, unsigned long long *__restr
 }
 // displacement level of an atom: ceil(|x - site| / 0.01a), rounded up like the host's pick_list (+1e-6 A), capped at 255
 __device__ __forceinline__ unsigned char disp_level(const double dist2, const double a) {
-    const double l = ceil((sqrt(dist2) + 1e-6) / (0.01 * a));
+    const double inv = 100.0 / a;                               // one division per thread, hoisted by the compiler where `a` is uniform
+    const double l = ceil(fma(sqrt(dist2), inv, 2e-6 * inv));    // 2e-6 A of slack: never below the host's ceil((d + 1e-6) / (0.01 a))
     return (unsigned char)(l > 255.0 ? 255 : (int)l);
 }
 // squared displacement of the atom from its ideal site after the drift (0 for vacant sites).
@@ -234,7 +237,9 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
     }
     const int lev = disp_level(dist, g.a);
     s.ulev[d] = (unsigned char)lev;
-    if (vp.hot && lev > vp.mark_T && atomicAdd(vp.mark_count, 1ULL) < MARK_CAP) {
+    // (a plain look first: once the cap is passed -- thermalisation transients, when most atoms lie above T -- nobody queues on
+    // the counter any more; it then stands above MARK_CAP, which is what tells the stencil kernels to ignore the map)
+    if (vp.hot && lev > vp.mark_T && *(volatile unsigned long long *)vp.mark_count <= MARK_CAP && atomicAdd(vp.mark_count, 1ULL) < MARK_CAP) {
         // a far-displaced atom (a few dozen of 2 M at 300 K): every cell within the stencil reach learns that the cheap
         // partner bound mark_T does not hold around it. The mark is the step's epoch byte, so the map is never cleared: a
         // stale byte that aliases 255 steps later only makes a warp keep the global bound (the safe side).

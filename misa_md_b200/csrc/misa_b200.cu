@@ -781,6 +781,7 @@ extern "C" int misa_b200_download_atoms(misa_b200_ctx *c, void *atoms) {
 extern "C" int misa_b200_sync(misa_b200_ctx *c) {
     REQ(c, MISA_B200_EINVAL, "null ctx");
     CU(cudaStreamSynchronize(c->stream));
+    REQ(!c->h_p2p_err || *c->h_p2p_err == 0, MISA_B200_ENCCL, "ghost push over peer memory: a neighbouring sub-box did not answer within the spin limit");
     return 0;
 }
 
@@ -1637,6 +1638,7 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
         TRY(launch_force(c, false, boundary));
     }
     CU(cudaEventSynchronize(c->ev_act));
+    REQ(!c->h_p2p_err || *c->h_p2p_err == 0, MISA_B200_ENCCL, "ghost push over peer memory: a neighbouring sub-box did not answer within the spin limit");
     c->inter_active = c->h_stepinfo[0] > 0;
     c->pipe_steps++;
     if (c->inter_active || c->h_counters[3] != 0) {
