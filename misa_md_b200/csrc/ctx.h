@@ -150,6 +150,7 @@ struct misa_b200_ctx {
     double *d_sendbuf[2] = {nullptr, nullptr}, *d_recvbuf[2] = {nullptr, nullptr};
     size_t halo_buf_elems = 0;
     // direct push of the composed ghost <- owned map into the neighbours' HBM (p2p.cuh)
+    int opt_late = 1;                     // wait for the neighbours' push inside the stencil kernels (interior units first)
     int opt_p2p = -1;                     // -1 / 1: whenever every surrounding sub-box is peer-mapped on this node; 0: NCCL send/recv
     bool p2p_active = false;
     int n_push = 0;

@@ -246,7 +246,7 @@ __device__ __forceinline__ double generic_force_pair(const double2 *__restrict__
 template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM, bool DILUTE = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
-        const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList()) {
+        const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList(), const LateWait lw = LateWait()) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
@@ -268,9 +268,12 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const int nt = tb.n_types; (void)nt;
     const double2 *__restrict__ g_herm = sp.g_elec[0];
     const size_t tstride = (size_t)tb.n_r + 1;
+    bool waited = lw.flags == nullptr;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
-        const int par = u >= upp;
-        const long long up = u - (par ? upp : 0);
+        int par;
+        long long up;
+        unit_split(rl, u, par, up);
+        if (!waited && u >= 2 * rl.split) { late_wait(lw, lane); waited = true; }
         const int d0 = region_unit_to_dev(g, rl, up, par, lane);
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
@@ -361,7 +364,7 @@ EAM_UNROLL(2)
 template <bool SINGLE, bool NOVAC, bool ACCUM, bool DILUTE = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
-          const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList()) {
+          const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList(), const LateWait lw = LateWait()) {
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
@@ -384,9 +387,12 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const int nt = tb.n_types; (void)nt;
     const double2 *__restrict__ g_herm = sp.g_elec[0];
     const size_t tstride = (size_t)tb.n_r + 1;
+    bool waited = lw.flags == nullptr;
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
-        const int par = u >= upp;
-        const long long up = u - (par ? upp : 0);
+        int par;
+        long long up;
+        unit_split(rl, u, par, up);
+        if (!waited && u >= 2 * rl.split) { late_wait(lw, lane); waited = true; }
         const int d0 = region_unit_to_dev(g, rl, up, par, lane);
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);

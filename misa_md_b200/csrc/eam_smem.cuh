@@ -162,7 +162,33 @@ __device__ __forceinline__ int unit_to_dev(const Geo &g, const long long u, cons
 //      six boundary slabs), so that interior cells can be computed while the ghost exchange is in flight --------
 #define EAM_MAX_REGIONS 7
 struct Region { int x0, y0, z0, nx, ny, nz; long long u0; };   // u0: first warp unit of this box (within one parity)
-struct RegionList { int n; long long units; Region r[EAM_MAX_REGIONS]; };  // units: warp units per parity
+struct RegionList { int n; long long units; Region r[EAM_MAX_REGIONS]; long long split; };  // units: warp units per parity
+// split > 0: region 0 is the interior and holds `split` units per parity; the launch then visits BOTH parities' interior units
+// before any boundary unit, so that a warp can wait for the neighbours' ghost push as late as possible (LateWait below)
+__device__ __forceinline__ void unit_split(const RegionList &rl, const long long u, int &par, long long &up) {
+    if (rl.split <= 0) { par = u >= rl.units; up = u - (par ? rl.units : 0); return; }
+    if (u < 2 * rl.split) { par = u >= rl.split; up = u - (par ? rl.split : 0); return; }
+    const long long v = u - 2 * rl.split, ub = rl.units - rl.split;
+    par = v >= ub;
+    up = rl.split + v - (par ? ub : 0);
+}
+// Ghost push of p2p.cuh consumed INSIDE the stencil kernel: interior units read no ghost site (nor any 32-byte sector that
+// holds one), so they run while the neighbours' stores are still in flight; the first boundary unit of a warp spins on the
+// arrive flags (ld.acquire.sys). The L1 / texture cache is cold for every sector with a ghost in it until then.
+struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; };
+__device__ __forceinline__ void late_wait(const LateWait &lw, const int lane) {
+    if (lane < 27 && ((lw.mask >> lane) & 1u)) {
+        const unsigned long long *w = lw.flags + 32 + lane;   // P2P_ARRIVE + code
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (v < lw.epoch && clock64() - t0 > 6000000000LL) { *(volatile unsigned int *)lw.err = 200u + lane; break; }
+        } while (v < lw.epoch);
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ int region_unit_to_dev(const Geo &g, const RegionList &rl, const long long u, const int p, const int lane) {
     int b = 0;
     while (b + 1 < rl.n && u >= rl.r[b + 1].u0) b++;

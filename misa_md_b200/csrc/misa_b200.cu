@@ -807,6 +807,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "sym")) c->opt_sym = value;
     else if (!strcmp(name, "p2p")) c->opt_p2p = value;
     else if (!strcmp(name, "mark")) c->opt_mark = value;
+    else if (!strcmp(name, "late")) c->opt_late = value;
     else if (!strcmp(name, "minor_staged")) c->opt_minor_staged = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
@@ -1110,6 +1111,20 @@ static RegionList make_regions(const Geo &g, int which) {
     if (which == 0 || !has_interior) { if (which != 1) add(0, 0, 0, g.nx, g.ny, g.nz); return rl; }
     const int ix = g.nx - 2 * g.gx, iy = g.ny - 2 * g.gy, iz = g.nz - 2 * g.gz;
     if (which == 1) { add(g.gx, g.gy, g.gz, ix, iy, iz); return rl; }
+    if (which == 3) {
+        // interior FIRST, then the slabs around it, for the in-kernel wait on the neighbours' ghost push (LateWait). The
+        // interior keeps 15 more cells from the x faces: its loads must not touch a 128-byte cache LINE that holds a ghost
+        // site (16 doubles along x: the line of a ghost reaches 15 owned cells into the row), or a stale copy of the ghost
+        // could sit in L1 / the texture cache when the boundary units read it after the wait
+        const int mx = g.gx + 15, jx = g.nx - 2 * mx;
+        if (jx <= 0) { add(0, 0, 0, g.nx, g.ny, g.nz); return rl; }
+        add(mx, g.gy, g.gz, jx, iy, iz);
+        rl.split = rl.units;
+        add(0, 0, 0, g.nx, g.ny, g.gz); add(0, 0, g.nz - g.gz, g.nx, g.ny, g.gz);
+        add(0, 0, g.gz, g.nx, g.gy, iz); add(0, g.ny - g.gy, g.gz, g.nx, g.gy, iz);
+        add(0, g.gy, g.gz, mx, iy, iz); add(g.nx - mx, g.gy, g.gz, mx, iy, iz);
+        return rl;
+    }
     add(0, 0, 0, g.nx, g.ny, g.gz); add(0, 0, g.nz - g.gz, g.nx, g.ny, g.gz);
     add(0, 0, g.gz, g.nx, g.gy, iz); add(0, g.ny - g.gy, g.gz, g.nx, g.gy, iz);
     add(0, g.gy, g.gz, g.gx, iy, iz); add(g.nx - g.gx, g.gy, g.gz, g.gx, iy, iz);
@@ -1140,8 +1155,8 @@ struct StencilOpt {                 // how one stencil launch deviates from "who
     int region = 0;                 // 0 whole, 1 interior, 2 boundary slabs
     const unsigned long long *dmax2 = nullptr;
     int reserve_sms = 0;            // leave this many SMs free (the persistent CTAs would otherwise starve the exchange kernels on stream2)
+    bool late = false;              // the ghost push this launch consumes has been issued but not waited for (p2p.cuh)
 };
-
 // ---- pair-symmetric passes (eam_sym.cuh) --------------------------------------------------------------------------
 // One species (or a dilute alloy, whose main loop is the majority species'), overwrite semantics, the whole sub-box in
 // one launch (the interior / boundary split of the overlapped exchange keeps the full-list kernels).
@@ -1150,6 +1165,20 @@ static bool sym_ok(const misa_b200_ctx *c, const StagePlan &sp, bool accum, cons
     return sp.single >= 0 || dilute_ok(c, sp, accum);
 }
 static bool sym_active(const misa_b200_ctx *c, const StagePlan &sp) { return sym_ok(c, sp, false, StencilOpt()); }
+// The wait for the neighbours' push goes INSIDE the stencil kernel when that kernel reads nothing but positions / df of its
+// neighbours through the texture path (no per-neighbour type loads: their 32-site sectors would need a 32-cell margin) and
+// the sub-box has an interior; otherwise it is a kernel of its own in front of the launch.
+static bool late_wait_ok(const misa_b200_ctx *c, const StagePlan &sp, bool planned, bool accum, const StencilOpt &so) {
+    if (!so.late || !c->opt_late || !planned || !c->opt_fast || !c->tex_all || accum || so.region != 0 || !no_vacancy(c)) return false;
+    if (!(sp.single >= 0 || dilute_ok(c, sp, accum)) || sym_ok(c, sp, accum, so)) return false;
+    return make_regions(c->geo, 3).split > 0;
+}
+static LateWait make_latewait(const misa_b200_ctx *c) {
+    LateWait lw;
+    lw.flags = c->d_flags; lw.epoch = c->p2p_epoch; lw.mask = c->p2p.mask; lw.err = c->d_p2p_err;
+    return lw;
+}
+
 static int sym_scratch(misa_b200_ctx *c) {
     const size_t need = (size_t)c->n_half * (((size_t)c->geo.n_ext + 31) / 32 * 32);
     if (c->pair_elems >= need) return 0;
@@ -1195,11 +1224,15 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
     Slot sl(c, MISA_B200_K_RHO);
     StagePlan sp;
     size_t sb;
-    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb)) {
+    const bool planned_any = make_plan(c, sp, sb);
+    const bool late = late_wait_ok(c, sp, planned_any, accum, so);
+    if (so.late && !late) TRY(p2p_wait(c, c->stream));   // the push this launch consumes: waited for in front of it
+    const LateWait lw = late ? make_latewait(c) : LateWait();
+    if (c->opt_fast && c->tex_all && planned_any) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-        const RegionList rl = make_regions(g, so.region);
+        const RegionList rl = make_regions(g, late ? 3 : so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;
         if (sym_ok(c, sp, accum, so)) {
@@ -1227,7 +1260,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         }
         if (dilute_ok(c, sp, accum)) {
             const MinorList ml = minor_list(c);
-#define RHO_D(N, F) k_rho_f<true, N, F, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml)
+#define RHO_D(N, F) k_rho_f<true, N, F, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml, lw)
             if (novac) { if (fuse_df) RHO_D(true, true); else RHO_D(true, false); }
             else { if (fuse_df) RHO_D(false, true); else RHO_D(false, false); }
 #undef RHO_D
@@ -1235,7 +1268,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
             CU(cudaGetLastError());
             return 0;
         }
-#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList())
+#define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw)
 #define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
         if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
 #undef RHO_FA
@@ -1320,6 +1353,10 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     Slot sl(c, MISA_B200_K_FORCE);
     StagePlan sp;
     size_t sb;
+    const bool planned_any = make_plan(c, sp, sb);
+    const bool late = late_wait_ok(c, sp, planned_any, accum, so);
+    if (so.late && !late) TRY(p2p_wait(c, c->stream));   // the push this launch consumes: waited for in front of it
+    const LateWait lw = late ? make_latewait(c) : LateWait();
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && sym_ok(c, sp, accum, so)) {
         TRY(sym_scratch(c));
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
@@ -1348,11 +1385,11 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-        const RegionList rl = make_regions(g, so.region);
+        const RegionList rl = make_regions(g, late ? 3 : so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         const MinorList ml = minor_list(c);
         if (rl.units > 0) {
-            if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml);
+            if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml, lw);
             else k_force_f<true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml);
             c->launches++;
             CU(cudaGetLastError());
@@ -1368,11 +1405,11 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-        const RegionList rl = make_regions(g, so.region);
+        const RegionList rl = make_regions(g, late ? 3 : so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;
 #define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); \
-                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); } while (0)
+                           else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw); } while (0)
         if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
 #undef FORCE_F
         c->launches++;
@@ -1606,16 +1643,20 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
             CU(cudaStreamWaitEvent(c->stream2, c->ev_v1, 0));
             TRY(activity_enqueue(c, c->stream2));
             CU(cudaEventRecord(c->ev_act, c->stream2));
-            TRY(halo_forward(c, true));
+            TRY(p2p_push(c, true, c->stream));
             CU(cudaStreamWaitEvent(c->stream, c->ev_act, 0));
+            whole.late = true;                      // the wait for the neighbours' pushes moves into the stencil kernels
+            TRY(launch_rho(c, true, false, whole));
+            TRY(p2p_push(c, false, c->stream));
+            TRY(launch_force(c, false, whole));
         } else {
             TRY(activity_enqueue(c, c->stream));
             CU(cudaEventRecord(c->ev_act, c->stream));
             TRY(halo_forward(c, true));
+            TRY(launch_rho(c, true, false, whole));
+            TRY(halo_forward(c, false));
+            TRY(launch_force(c, false, whole));
         }
-        TRY(launch_rho(c, true, false, whole));
-        TRY(halo_forward(c, false));
-        TRY(launch_force(c, false, whole));
         // ghost x and df are free for the next step's two exchanges -- only when that step follows inside this call:
         // between calls the host may run readers of the ghosts (thermo, dump) that a neighbour's next push must not overtake
         if (defer_out) TRY(p2p_post_ready(c, 2, c->stream));

@@ -221,9 +221,11 @@ static int p2p_setup(misa_b200_ctx *c) {
 }
 
 // one ghost exchange, collective over the sub-boxes like the NCCL path:
-//   [ready signal, unless p2p_post_ready sent it ahead] -> push (waits for the destinations' ready, last CTA signals arrive)
-//   -> wait for every origin's arrive
-static int p2p_exchange(misa_b200_ctx *c, bool positions, cudaStream_t st) {
+//   p2p_push: [ready signal, unless p2p_post_ready sent it ahead] -> push (waits for the destinations' ready, last CTA
+//             signals arrive)
+//   p2p_wait: wait for every origin's arrive -- as a tiny kernel, or inside the consuming stencil kernel right before its
+//             first boundary unit (eam_smem.cuh:LateWait), which hides the neighbours' latency and skew behind the interior
+static int p2p_push(misa_b200_ctx *c, bool positions, cudaStream_t st) {
     const unsigned long long e = ++c->p2p_epoch;
     if (c->p2p_ready_sent < e) {
         k_p2p_ready<<<1, 32, 0, st>>>(c->p2p, e);
@@ -234,10 +236,19 @@ static int p2p_exchange(misa_b200_ctx *c, bool positions, cudaStream_t st) {
     unsigned int *done = reinterpret_cast<unsigned int *>(c->d_flags + P2P_FLAG_WORDS - 1);
     if (positions) k_p2p_push_x<<<nb, MISA_BLOCK, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
     else k_p2p_push_df<<<nb, MISA_BLOCK, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
-    k_p2p_wait_arrive<<<1, 32, 0, st>>>(c->p2p, e, c->d_flags, c->d_p2p_err);
-    c->launches += 2;
+    c->launches++;
     CU(cudaGetLastError());
     return 0;
+}
+static int p2p_wait(misa_b200_ctx *c, cudaStream_t st) {
+    k_p2p_wait_arrive<<<1, 32, 0, st>>>(c->p2p, c->p2p_epoch, c->d_flags, c->d_p2p_err);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+static int p2p_exchange(misa_b200_ctx *c, bool positions, cudaStream_t st) {
+    TRY(p2p_push(c, positions, st));
+    return p2p_wait(c, st);
 }
 // Called right after the last reader of this sub-box's ghosts in a step (the force kernel of the sync-free step): frees
 // the ghosts for the next `ahead` exchanges, so that the neighbours' next pushes find the flag already there.

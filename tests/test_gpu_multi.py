@@ -115,6 +115,27 @@ def test_two_gpus_direct_push_equals_staged_nccl_exchange(tmp_path):
             assert np.array_equal(out["p2p"][r][fld], out["nccl"][r][fld]), (r, fld)
 
 
+def test_two_gpus_wait_for_the_push_inside_the_stencil_kernels(tmp_path):
+    """Sub-boxes long enough in x (40 cells) to have an interior: rho / force start on it while the neighbour's push is in
+    flight and wait for the arrive flags right before their first boundary unit. Same bits as waiting in front of the
+    launch, and the oracle's trajectory."""
+    out = {}
+    for name, opts in (("late", ""), ("front", "late=0")):
+        d = tmp_path / name
+        d.mkdir()
+        w = _run(d, (80, 8, 8), (2, 1, 1), (1, 0, 0), steps=6, opts=opts)
+        _compare(d, w, 1e-12, 1e-9)
+        w.close()
+        out[name] = [np.load(os.path.join(str(d), "lat%d.npy" % r)) for r in range(2)]
+        flags = [np.load(os.path.join(str(d), "p2p%d.npy" % r)) for r in range(2)]
+        assert all(f[1] == 0 for f in flags)
+        if flags[0][0] != 1:
+            pytest.skip("no peer access between the two GPUs: the NCCL path ran")
+    for r in range(2):
+        for fld in ("type", "x", "v", "f", "rho", "df"):
+            assert np.array_equal(out["late"][r][fld], out["front"][r][fld]), (r, fld)
+
+
 def test_two_gpus_pka_migrates_across_sub_boxes(tmp_path):
     """PKA launched next to the sub-box interface: inter atoms cross ranks (exchangeInter) and act as ghost
     inter atoms on the neighbour (borderInter + the inter part of the df halo)."""
