@@ -183,15 +183,27 @@ int misa_b200_pass_force(misa_b200_ctx *ctx);   /* latForce (+interForce) */
 int misa_b200_pass_verlet1(misa_b200_ctx *ctx); /* NewtonMotion::firststep + atom::decide */
 int misa_b200_pass_verlet2(misa_b200_ctx *ctx); /* NewtonMotion::secondstep */
 
-/* options: 0 = off, 1 = on. "prune": use the 112-offset stencil whenever the 0.2a displacement invariant of
- * atom::decide (atom.cpp:42) is verified on the device (default on); "fuse": rho+df fused when no inter atoms. */
+/* options (A/B switches; the defaults are the production path; also settable as MISA_B200_OPTS="name=value,..."):
+ *   "prune" 1  stencil lists pruned by the measured displacements whenever the 0.2a invariant of atom::decide (atom.cpp:42)
+ *              holds on the device: per warp, a prefix of the distance-sorted full list
+ *   "mark" 1   partner bound of that pruning from the cells marked by far-displaced atoms instead of the global maximum
+ *   "fuse" 1   rho + df in one kernel when no inter atoms; "fuse_verlet" 1: second half-kick applied by the next firststep
+ *   "smem" 1 / "fast" 1 / "tex" 1 / "novac" 1 / "dilute" 1   kernel generations and their fast paths (csrc/eam_*.cuh)
+ *   "sym" 0    pair-symmetric passes (each near pair evaluated once): measured slower; "minor_staged" 0: likewise
+ *   "pipe" 1   step without a host round trip on its critical path; "overlap" -1, "reserve" 8: interior / boundary split
+ *              of the stencil launches around a staged NCCL exchange
+ *   "p2p" -1   ghost exchange by direct stores into the neighbours' HBM when all of them are peer-mapped (0: NCCL);
+ *   "late" 1   wait for the neighbours' push inside the stencil kernels (interior units first) */
 int misa_b200_set_option(misa_b200_ctx *ctx, const char *name, int value);
 
-/* read-only introspection (tests, benches): "n_off", "n_full", "dmax", "single", "novac", "smem_bytes" */
+/* read-only introspection (tests, benches): "n_off", "n_full", "n_half", "dmax", "single", "novac", "dilute", "n_minor", "sym",
+ * "smem_bytes", "pipe_steps", "pipe_redo", "mark_level", "mark_count", "p2p", "p2p_error" */
 int misa_b200_query(misa_b200_ctx *ctx, const char *name, double *value);
 
-/* ---- multi-GPU: one sub-box per GPU, NCCL send/recv between face neighbours (replaces libcomm's
- *      comm::neiSendReceive over MPI; call sites atom.cpp:114,131,145, atom_list.cpp:45,53) ----- */
+/* ---- multi-GPU: one sub-box per GPU (replaces libcomm's comm::neiSendReceive over MPI; call sites atom.cpp:114,131,145,
+ *      atom_list.cpp:45,53). comm_init builds the NCCL communicator and, when every surrounding sub-box is on a
+ *      peer-accessible GPU of this node, maps their arrays (CUDA IPC) for the direct ghost push of csrc/p2p.cuh;
+ *      otherwise ghosts travel as staged NCCL send/recv between face neighbours ----- */
 int misa_b200_comm_unique_id(void *out128);
 int misa_b200_comm_init(misa_b200_ctx *ctx, const void *unique_id128, int rank, int n_ranks);
 int misa_b200_comm_destroy(misa_b200_ctx *ctx);

@@ -123,7 +123,7 @@ struct misa_b200_ctx {
     long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant
     bool seen_offlattice = false;         // a run-away / inter atom was reported by any sub-box since the last census
     int opt_fuse_verlet = 1;              // inside a multi-step call: second half-kick of step k folded into k_verlet1 of step k+1
-    int opt_dilute = 1;                   // dilute-alloy kernels (eam_dilute.cuh) when one species holds >= 90 % of the sites
+    int opt_dilute = 1;                   // dilute-alloy kernels (eam_fast.cuh, DILUTE variants) when one species holds >= 90 % of the sites
     // static minority-neighbour lists (eam_fast.cuh, built by prepare(); valid until atoms are replaced or anything runs away)
     unsigned char *d_mcount = nullptr, *d_mentry = nullptr;
     int *d_minor = nullptr, *d_minor_count = nullptr; // device indices of the owned minority-species atoms

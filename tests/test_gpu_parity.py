@@ -281,7 +281,7 @@ def test_compat_hooks_match_cpu_branch():
 
 @pytest.mark.parametrize("ratio,vac", [((97, 2, 1), 0), ((92, 5, 3), 7), ((3, 95, 2), 0)])
 def test_dilute_alloy_kernels_match_oracle(ratio, vac):
-    """eam_dilute.cuh (majority tables branch-free, minority pairs listed and corrected, minority atoms one warp
+    """Dilute-alloy kernels of eam_fast.cuh (majority tables branch-free, minority pairs listed and corrected, minority atoms one warp
     each) against the oracle and against the general multi-species kernels, over a few steps."""
     st = cm.make_state((10, 9, 11), ratio=ratio, sigma=0.06, vacancies=vac)
     w = cm.oracle_world(st)
