@@ -101,6 +101,16 @@ int misa_b200_plan_offsets(const misa_b200_domain *dom, int cut_lattice, double 
                            int64_t *out, size_t cap, size_t *n);
 int misa_b200_plan_halo(const misa_b200_domain *dom, int dim, int dir, int64_t *send, int64_t *recv, size_t cap,
                         size_t *n, double shift[3]);
+/* Host-only: how the stencil kernels loop the offsets of plan_offsets (csrc/misa_b200.cu:plan_stencil). `sorted` = the
+ * full list of central parity `parity` (reference index space) in device order: the near group first (sites closer than
+ * crf + 0.05 lattice constants; its first n_half entries are one of each +v / -v pair, the next n_half the mirrors in the
+ * order lower_slot[] names), then the rest by ascending site separation; site_r2 = squared site separation / a^2 of each
+ * entry; prefix[L], L = 0..40 = entries a warp loops when (largest displacement level among its atoms) + (bound on the
+ * partner's) = L, one level = 0.01 a: every offset whose sites are closer than (crf + 0.01 L) a is inside that prefix,
+ * which is what makes the pruning exact. No reference counterpart (the CPU loops all 114 half offsets, atom.cpp:173). */
+int misa_b200_plan_stencil(const misa_b200_domain *dom, int cut_lattice, double cutoff_radius_factor, int parity,
+                           int64_t *sorted, double *site_r2, size_t cap, size_t *n, int32_t *n_near, int32_t *n_half,
+                           int32_t prefix[41], int32_t *lower_slot);
 /* Host-only: the three staged exchanges above composed into ONE ghost <- owned map (what the direct NVLink push of
  * the multi-GPU path applies, csrc/p2p.cuh). Entry i: site dst[i] of this sub-box receives site src[i] of the sub-box
  * at offset (sx, sy, sz), code[i] = (sx+1) + 3 (sy+1) + 9 (sz+1); all sub-boxes have the same shape, so read backwards

@@ -20,7 +20,7 @@ K_COUNT = len(K_NAMES)
 EXPORTS = [
     "misa_b200_env_init", "misa_b200_env_clean", "misa_b200_device_count", "misa_b200_last_error",
     "misa_b200_create", "misa_b200_destroy", "misa_b200_set_neighbour_offsets", "misa_b200_make_neighbour_offsets",
-    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_plan_push", "misa_b200_set_potential",
+    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_plan_push", "misa_b200_plan_stencil", "misa_b200_set_potential",
     "misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc",
     "misa_b200_site_count", "misa_b200_host_register", "misa_b200_host_unregister",
     "misa_b200_upload_atoms", "misa_b200_download_atoms", "misa_b200_upload_inter", "misa_b200_download_inter",
@@ -83,6 +83,8 @@ def load(build=True):
     L.misa_b200_get_neighbour_offsets.argtypes = [vp, i, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.misa_b200_plan_offsets.argtypes = [C.POINTER(Domain), i, d, i, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.misa_b200_plan_halo.argtypes = [C.POINTER(Domain), i, i, i64p, i64p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(d * 3)]
+    L.misa_b200_plan_stencil.argtypes = [C.POINTER(Domain), i, d, i, i64p, C.POINTER(d), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.misa_b200_plan_push.argtypes = [C.POINTER(Domain), i64p, i64p, C.POINTER(C.c_int8), C.c_size_t, C.POINTER(C.c_size_t), vp]
     L.misa_b200_set_potential.argtypes = [vp, i, C.POINTER(Table), C.POINTER(Table), C.POINTER(Table)]
     for fn in ("misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc"):
@@ -183,6 +185,25 @@ def plan_halo(dom, dim, direction):
     p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
     _ck(L.misa_b200_plan_halo(C.byref(dom), dim, direction, p(send), p(recv), n.value, C.byref(n), C.byref(shift)))
     return send, recv, np.array(list(shift))
+
+
+def plan_stencil(dom, parity, cut_lattice=None, crf=None):
+    """Host-only: dict(sorted, site_r2, n_near, n_half, prefix[41], lower_slot) -- include/misa_b200.h:misa_b200_plan_stencil."""
+    import math
+    L = load()
+    crf = dom.cutoff_radius_factor if crf is None else crf
+    cut_lattice = int(math.ceil(crf)) if cut_lattice is None else cut_lattice
+    n = C.c_size_t()
+    _ck(L.misa_b200_plan_stencil(C.byref(dom), cut_lattice, crf, parity, None, None, 0, C.byref(n), None, None, None, None))
+    srt = np.zeros(n.value, dtype=np.int64)
+    r2 = np.zeros(n.value, dtype=np.float64)
+    near, half = C.c_int32(), C.c_int32()
+    prefix = np.zeros(41, dtype=np.int32)
+    slot = np.zeros(n.value, dtype=np.int32)
+    _ck(L.misa_b200_plan_stencil(C.byref(dom), cut_lattice, crf, parity, srt.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 r2.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n), C.byref(near), C.byref(half),
+                                 prefix.ctypes.data_as(C.POINTER(C.c_int32)), slot.ctypes.data_as(C.POINTER(C.c_int32))))
+    return dict(sorted=srt, site_r2=r2, n_near=near.value, n_half=half.value, prefix=prefix, lower_slot=slot[:half.value])
 
 
 def plan_push(dom):

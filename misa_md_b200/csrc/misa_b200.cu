@@ -422,37 +422,49 @@ static double off_site_r2(long long off, int p, const Geo &g) {
     return X * X + Y * Y + Z * Z;
 }
 
-static int upload_offsets(misa_b200_ctx *c) {
-    const Geo &g = c->geo;
-    REQ(c->ref_off[0].size() == c->ref_off[1].size() && !c->ref_off[0].empty(), MISA_B200_EINVAL,
+// Everything the stencil kernels need from the reference's four offset vectors, planned on the HOST (no device): the
+// distance-sorted full list per parity, its near / half split, the prefix lengths per pair displacement level, the
+// lower-neighbour table of the pair-symmetric passes and the second generation's per-level lists.
+struct StencilPlan {
+    int n_full = 0, near_full = 0, n_half = 0;
+    std::vector<int> full;                  // [2][n_full] device-index offsets, sorted
+    std::vector<long long> sorted_ref[2];   // the same entries in the reference's index space
+    std::vector<double> site_r2[2];         // squared SITE separation of each entry, units of a^2
+    int prefix_n[misa_b200_ctx::kPairLevels] = {0};
+    std::vector<int2> lo;                   // [2][n_half]
+    int sym_lo[3] = {0, 0, 0}, sym_hi[3] = {0, 0, 0};
+    std::vector<int> levels;
+    size_t level_ofs[misa_b200_ctx::kLevels] = {0};
+    int level_n[misa_b200_ctx::kLevels] = {0}, level_near[misa_b200_ctx::kLevels] = {0};
+};
+static int plan_stencil(const Geo &g, const double crf, const std::vector<int64_t> ref_off[2], StencilPlan &sp) {
+    REQ(ref_off[0].size() == ref_off[1].size() && !ref_off[0].empty(), MISA_B200_EINVAL,
         "neighbour offsets: even/odd lists must be non-empty and of equal length");
-    c->n_full = (int)c->ref_off[0].size();
-    std::vector<int> full(2 * (size_t)c->n_full), levels;
+    const int n_full = sp.n_full = (int)ref_off[0].size();
+    sp.full.assign(2 * (size_t)n_full, 0);
     // device lists are PARTITIONED by site separation (the sums do not depend on the order; the reference order stays
-    // in ref_off for the ABI and the inter-atom kernels): the leading `near` entries -- sites at least 0.1a inside the
-    // cutoff -- are in range for practically every atom and are evaluated without a branch (eam_fast.cuh)
-    std::vector<double> site_r2[2];
+    // in ref_off for the ABI and the inter-atom kernels): the leading `near` entries are in range for practically every
+    // atom and are evaluated without a branch (eam_fast.cuh)
     {
         // near: shells that reach inside the cutoff at thermal displacements -- up to 0.05a OUTSIDE it, which takes in the
         // <200> shell of bcc (2.0a against crf = 1.961: 16 % of those pairs are in range at 300 K, i.e. practically every
         // warp-wide vote of the far loop was true for them anyway)
-        const double near_lim = c->dom.cutoff_radius_factor + 0.05;
+        const double near_lim = crf + 0.05;
         int near[2] = {0, 0}, half[2] = {0, 0};
-        std::vector<long long> sorted_ref[2];
         for (int p = 0; p < 2; p++) {
-            std::vector<int> perm(c->n_full);
-            std::vector<double> r2(c->n_full);
-            for (int q = 0; q < c->n_full; q++) { perm[q] = q; r2[q] = off_site_r2(c->ref_off[p][q], p, g); }
+            std::vector<int> perm(n_full);
+            std::vector<double> r2(n_full);
+            for (int q = 0; q < n_full; q++) { perm[q] = q; r2[q] = off_site_r2(ref_off[p][q], p, g); }
             // near group first; inside a group keep the reference's order (ascending memory offset: consecutive
             // iterations then touch neighbouring lines, which is what keeps the L1 hit rate up)
             // ... and inside the near group the UPPER half first: the pair-symmetric passes (eam_sym.cuh) evaluate only
-            // those. "Upper" is the sign of the real-space site separation (z, then y, then x) -- the same 29 vectors for
+            // those. "Upper" is the sign of the real-space site separation (z, then y, then x) -- the same vectors for
             // both sub-lattices of the Bravais lattice, whereas the reference's index-order half list
             // (neighbour_index.inl:79-92) splits the near shells 21 : 37 between even and odd x. Any antisymmetric
             // choice visits every pair exactly once; the per-atom sums do not depend on it.
             auto upper = [&](int q) {
                 long long dx, dy, dz;
-                off_decode(c->ref_off[p][q], g, dx, dy, dz);
+                off_decode(ref_off[p][q], g, dx, dy, dz);
                 const int h2 = (dx & 1) ? (p == 0 ? 1 : -1) : 0;             // twice the half-cell shift of an odd dx
                 const long long X = dx, Y = 2 * dy + h2, Z = 2 * dz + h2;     // twice the separation in units of a
                 return Z > 0 || (Z == 0 && (Y > 0 || (Y == 0 && X > 0)));
@@ -464,22 +476,22 @@ static int upload_offsets(misa_b200_ctx *c) {
                 if (cls(a) != cls(b)) return cls(a) < cls(b);
                 return cls(a) == 2 && r2[a] < r2[b];
             });
-            site_r2[p].resize(c->n_full);
-            sorted_ref[p].resize(c->n_full);
-            for (int q = 0; q < c->n_full; q++) {
-                full[(size_t)p * c->n_full + q] = ref_off_to_dev(c->ref_off[p][perm[q]], p, g.H);
-                site_r2[p][q] = r2[perm[q]];
-                sorted_ref[p][q] = c->ref_off[p][perm[q]];
+            sp.site_r2[p].resize(n_full);
+            sp.sorted_ref[p].resize(n_full);
+            for (int q = 0; q < n_full; q++) {
+                sp.full[(size_t)p * n_full + q] = ref_off_to_dev(ref_off[p][perm[q]], p, g.H);
+                sp.site_r2[p][q] = r2[perm[q]];
+                sp.sorted_ref[p][q] = ref_off[p][perm[q]];
                 if (cls(perm[q]) < 2) near[p]++;
                 if (cls(perm[q]) == 0) half[p]++;
             }
         }
-        c->near_full = std::min(near[0], near[1]);
+        sp.near_full = std::min(near[0], near[1]);
         // pair-symmetric passes: both parities must agree on the split, every lower near offset of parity pj must be the
         // mirror of an upper near offset of the neighbour's parity, and the sites around the owned box that own such a
         // pair must exist in the ghost shell
-        c->n_half = 0;
-        cudaFree(c->d_lo_tab); c->d_lo_tab = nullptr;
+        sp.n_half = 0;
+        sp.lo.clear();
         if (near[0] == near[1] && half[0] == half[1] && 2 * half[0] == near[0] && half[0] > 0) {
             const int nh = half[0];
             std::vector<int2> lo(2 * (size_t)nh);
@@ -487,12 +499,12 @@ static int upload_offsets(misa_b200_ctx *c) {
             int elo[3] = {0, 0, 0}, ehi[3] = {0, 0, 0};
             for (int pj = 0; pj < 2 && ok; pj++)
                 for (int m = 0; m < nh && ok; m++) {
-                    const long long o = sorted_ref[pj][nh + m];            // lower near entry: i = j + o
+                    const long long o = sp.sorted_ref[pj][nh + m];         // lower near entry: i = j + o
                     const int pi = pj ^ (int)(o & 1);
                     int slot = -1;
-                    for (int k = 0; k < nh; k++) if (sorted_ref[pi][k] == -o) slot = k;
+                    for (int k = 0; k < nh; k++) if (sp.sorted_ref[pi][k] == -o) slot = k;
                     if (slot < 0) { ok = false; break; }
-                    lo[(size_t)pj * nh + m] = make_int2(full[(size_t)pj * c->n_full + nh + m], slot);
+                    lo[(size_t)pj * nh + m] = make_int2(sp.full[(size_t)pj * n_full + nh + m], slot);
                     long long dx, dy, dz;
                     off_decode(o, g, dx, dy, dz);
                     const long long dc[3] = {(pj + dx) >> 1, dy, dz};      // cells from j to its lower neighbour
@@ -501,41 +513,56 @@ static int upload_offsets(misa_b200_ctx *c) {
             const int gh[3] = {g.gx, g.gy, g.gz};
             for (int k = 0; k < 3; k++) ok = ok && elo[k] <= gh[k] && ehi[k] <= gh[k];
             if (ok) {
-                c->n_half = nh;
-                for (int k = 0; k < 3; k++) { c->sym_lo[k] = elo[k]; c->sym_hi[k] = ehi[k]; }
-                TRY(dmalloc(&c->d_lo_tab, lo.size()));
-                CU(cudaMemcpy(c->d_lo_tab, lo.data(), lo.size() * sizeof(int2), cudaMemcpyHostToDevice));
+                sp.n_half = nh;
+                for (int k = 0; k < 3; k++) { sp.sym_lo[k] = elo[k]; sp.sym_hi[k] = ehi[k]; }
+                sp.lo = lo;
             }
         }
     }
     // prefix lengths of the sorted full list by PAIR displacement level: sites closer than (crf + 0.01 L) a
     for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) {
-        const double lim = c->dom.cutoff_radius_factor + 0.01 * L + 1e-9;
+        const double lim = crf + 0.01 * L + 1e-9;
         int n[2] = {0, 0};
         for (int p = 0; p < 2; p++)
-            for (int q = 0; q < c->n_full; q++)
-                if (q < c->near_full || site_r2[p][q] < lim * lim) n[p] = q + 1;
-        c->prefix_n[L] = std::max(n[0], n[1]);
+            for (int q = 0; q < n_full; q++)
+                if (q < sp.near_full || sp.site_r2[p][q] < lim * lim) n[p] = q + 1;
+        sp.prefix_n[L] = std::max(n[0], n[1]);
     }
     // pairs of LATTICE atoms can only be within the cutoff if their sites are closer than crf + 2*dmax/a;
     // atom::decide keeps dmax <= 0.2a (reference src/atom.cpp:42), the device measures the actual value.
+    sp.levels.clear();
     for (int L = 0; L < misa_b200_ctx::kLevels; L++) {
-        const double lim = c->dom.cutoff_radius_factor + 0.02 * L + 1e-9;
+        const double lim = crf + 0.02 * L + 1e-9;
         int n[2] = {0, 0};
-        c->level_ofs[L] = levels.size();
+        sp.level_ofs[L] = sp.levels.size();
         for (int p = 0; p < 2; p++)
-            for (int q = 0; q < c->n_full; q++)
-                if (site_r2[p][q] < lim * lim) { levels.push_back(full[(size_t)p * c->n_full + q]); n[p]++; }
+            for (int q = 0; q < n_full; q++)
+                if (sp.site_r2[p][q] < lim * lim) { sp.levels.push_back(sp.full[(size_t)p * n_full + q]); n[p]++; }
         REQ(n[0] == n[1], MISA_B200_EINVAL, "neighbour offsets: pruned lists differ in length");
-        c->level_n[L] = n[0];
-        c->level_near[L] = std::min(c->near_full, n[0]);
+        sp.level_n[L] = n[0];
+        sp.level_near[L] = std::min(sp.near_full, n[0]);
+    }
+    return MISA_B200_OK;
+}
+static int upload_offsets(misa_b200_ctx *c) {
+    StencilPlan sp;
+    const std::vector<int64_t> ref[2] = {c->ref_off[0], c->ref_off[1]};
+    TRY(plan_stencil(c->geo, c->dom.cutoff_radius_factor, ref, sp));
+    c->n_full = sp.n_full; c->near_full = sp.near_full; c->n_half = sp.n_half;
+    for (int k = 0; k < 3; k++) { c->sym_lo[k] = sp.sym_lo[k]; c->sym_hi[k] = sp.sym_hi[k]; }
+    for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) c->prefix_n[L] = sp.prefix_n[L];
+    for (int L = 0; L < misa_b200_ctx::kLevels; L++) { c->level_ofs[L] = sp.level_ofs[L]; c->level_n[L] = sp.level_n[L]; c->level_near[L] = sp.level_near[L]; }
+    cudaFree(c->d_lo_tab); c->d_lo_tab = nullptr;
+    if (sp.n_half > 0) {
+        TRY(dmalloc(&c->d_lo_tab, sp.lo.size()));
+        CU(cudaMemcpy(c->d_lo_tab, sp.lo.data(), sp.lo.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
     cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
     c->d_off_full = c->d_off_levels = nullptr;
-    TRY(dmalloc(&c->d_off_full, full.size()));
-    TRY(dmalloc(&c->d_off_levels, levels.size()));
-    CU(cudaMemcpy(c->d_off_full, full.data(), full.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_off_levels, levels.data(), levels.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TRY(dmalloc(&c->d_off_full, sp.full.size()));
+    TRY(dmalloc(&c->d_off_levels, sp.levels.size()));
+    CU(cudaMemcpy(c->d_off_full, sp.full.data(), sp.full.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_off_levels, sp.levels.data(), sp.levels.size() * sizeof(int), cudaMemcpyHostToDevice));
     c->have_off = true;
     return MISA_B200_OK;
 }
@@ -597,6 +624,27 @@ extern "C" int misa_b200_plan_offsets(const misa_b200_domain *dom, int cut_latti
     return MISA_B200_OK;
 }
 
+extern "C" int misa_b200_plan_stencil(const misa_b200_domain *dom, int cut_lattice, double crf, int parity, int64_t *sorted, double *site_r2,
+                                      size_t cap, size_t *n, int32_t *n_near, int32_t *n_half, int32_t prefix[41], int32_t *lower_slot) {
+    REQ(dom && n && parity >= 0 && parity < 2, MISA_B200_EINVAL, "misa_b200_plan_stencil: bad argument");
+    Geo g;
+    REQ(geo_from_domain(dom, g) == 0, MISA_B200_EINVAL, "misa_b200_plan_stencil: bad sub-box sizes");
+    std::vector<int64_t> v[4];
+    make_offsets_host(g, cut_lattice, crf, v);
+    const std::vector<int64_t> ref[2] = {v[0], v[1]};
+    StencilPlan sp;
+    TRY(plan_stencil(g, crf, ref, sp));
+    *n = (size_t)sp.n_full;
+    for (size_t i = 0; i < std::min(cap, *n); i++) {
+        if (sorted) sorted[i] = sp.sorted_ref[parity][i];
+        if (site_r2) site_r2[i] = sp.site_r2[parity][i];
+    }
+    if (n_near) *n_near = sp.near_full;
+    if (n_half) *n_half = sp.n_half;
+    if (prefix) for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) prefix[L] = sp.prefix_n[L];
+    if (lower_slot) for (int m = 0; m < sp.n_half; m++) lower_slot[m] = sp.lo[(size_t)parity * sp.n_half + m].y;
+    return MISA_B200_OK;
+}
 extern "C" int misa_b200_plan_halo(const misa_b200_domain *dom, int dim, int dir, int64_t *send, int64_t *recv, size_t cap,
                                    size_t *n, double shift[3]) {
     REQ(dom && n && dim >= 0 && dim < 3 && dir >= 0 && dir < 2, MISA_B200_EINVAL, "misa_b200_plan_halo: bad argument");

@@ -172,3 +172,50 @@ def test_direct_push_map_equals_the_staged_exchange(phase, grid, pot):
         assert np.array_equal(got[r]["type"], ref["type"])
         assert np.array_equal(got[r]["x"].view(np.uint64), ref["x"].view(np.uint64))   # incl. the image shifts, bit for bit
     w.close()
+
+
+@pytest.mark.parametrize("phase,grid,coord", CASES[:4])
+def test_stencil_plan_is_a_permutation_with_exact_prefixes(phase, grid, coord):
+    """misa_b200_plan_stencil: what the stencil kernels loop. (1) a permutation of NeighbourIndex::make's full list (so the
+    un-pruned sums are the reference's); (2) every pruned list is a prefix that contains EVERY offset whose sites are closer
+    than (crf + 0.01 L) a -- the exactness of the per-warp pruning rests on this; (3) the near group is split into one of
+    each +v / -v pair and its mirrors, and lower_slot pairs them up (pair-symmetric passes)."""
+    dom = capi.make_domain(phase, grid, coord, A, CRF)
+    sx = 2 * (dom.sub_box_lattice_size[0] + 2 * dom.lattice_size_ghost[0])
+    sy = dom.sub_box_lattice_size[1] + 2 * dom.lattice_size_ghost[1]
+
+    def sep2(off, parity):   # squared site separation in units of a^2, from the doubled-x linear offset
+        dx = ((off % sx) + sx + sx // 2) % sx - sx // 2
+        r = (off - dx) // sx
+        dy = ((r % sy) + sy + sy // 2) % sy - sy // 2
+        dz = (r - dy) // sy
+        h = (0.5 if parity == 0 else -0.5) if dx & 1 else 0.0
+        return (0.5 * dx) ** 2 + (dy + h) ** 2 + (dz + h) ** 2, (dx, 2 * dy + int(2 * h), 2 * dz + int(2 * h))
+
+    plans = [capi.plan_stencil(dom, p) for p in range(2)]
+    for p, pl in enumerate(plans):
+        ref = capi.plan_offsets(dom, p)
+        assert len(pl["sorted"]) == len(ref) == 228
+        assert np.array_equal(np.sort(pl["sorted"]), np.sort(ref))
+        r2 = np.array([sep2(int(o), p)[0] for o in pl["sorted"]])
+        assert np.allclose(r2, pl["site_r2"], rtol=0, atol=1e-12)
+        near, half = pl["n_near"], pl["n_half"]
+        assert near == 2 * half and half > 0
+        assert np.all(r2[:near] < (CRF + 0.05) ** 2) and np.all(r2[near:] >= (CRF + 0.05) ** 2)
+        assert np.all(np.diff(r2[near:]) >= 0)                      # the far part is sorted by separation
+        prefix = pl["prefix"]
+        assert np.all(np.diff(prefix) >= 0) and prefix[0] >= near and prefix[-1] <= 228
+        for L in range(41):
+            inside = r2 < (CRF + 0.01 * L) ** 2
+            assert np.all(np.nonzero(inside)[0] < prefix[L]), L     # nothing that could be in range is cut off
+        # decide() keeps every atom within 0.2a of its site: level 40 must hold every pair that can ever be in range
+        assert prefix[40] >= np.count_nonzero(r2 < (CRF + 0.4) ** 2)
+    for pj, pl in enumerate(plans):
+        half = pl["n_half"]
+        for m in range(half):
+            o = int(pl["sorted"][half + m])                          # a lower near offset of parity pj: neighbour i = j + o
+            pi = pj ^ (o & 1)
+            assert int(plans[pi]["sorted"][pl["lower_slot"][m]]) == -o
+        vec = [sep2(int(o), pj)[1] for o in pl["sorted"][:half]]
+        assert all(v[2] > 0 or (v[2] == 0 and (v[1] > 0 or (v[1] == 0 and v[0] > 0))) for v in vec)
+        assert sorted(vec) == sorted(tuple(-c for c in sep2(int(o), pj)[1]) for o in pl["sorted"][half:2 * half])
