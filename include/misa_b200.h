@@ -111,6 +111,15 @@ int misa_b200_plan_halo(const misa_b200_domain *dom, int dim, int dir, int64_t *
 int misa_b200_plan_stencil(const misa_b200_domain *dom, int cut_lattice, double cutoff_radius_factor, int parity,
                            int64_t *sorted, double *site_r2, size_t cap, size_t *n, int32_t *n_near, int32_t *n_half,
                            int32_t prefix[41], int32_t *lower_slot);
+/* Host-only: the boxes of owned cells one stencil launch covers (x0,y0,z0,nx,ny,nz). which = 0 the whole sub-box, 1 its
+ * interior (no ghost within the stencil reach), 2 the six slabs around that interior (the interior / boundary split of the
+ * overlapped NCCL exchange), 3 interior FIRST then the slabs in one launch, the interior kept 15 more cells from the x faces
+ * (no 128-byte line with a ghost in it is touched before the in-kernel wait for the neighbours' push). */
+int misa_b200_plan_regions(const misa_b200_domain *dom, int which, int32_t boxes[7][6], int32_t *n_boxes, int64_t *units,
+                           int64_t *split);
+/* ... and the order in which such a launch visits its 2 * units warp units: u -> (sub-lattice, unit within plan_regions'
+ * numbering). which = 3: the interior units of BOTH sub-lattices come before any boundary unit. */
+int misa_b200_plan_unit_order(const misa_b200_domain *dom, int which, int64_t u, int32_t *parity, int64_t *unit);
 /* Host-only: the three staged exchanges above composed into ONE ghost <- owned map (what the direct NVLink push of
  * the multi-GPU path applies, csrc/p2p.cuh). Entry i: site dst[i] of this sub-box receives site src[i] of the sub-box
  * at offset (sx, sy, sz), code[i] = (sx+1) + 3 (sy+1) + 9 (sz+1); all sub-boxes have the same shape, so read backwards

@@ -20,7 +20,7 @@ K_COUNT = len(K_NAMES)
 EXPORTS = [
     "misa_b200_env_init", "misa_b200_env_clean", "misa_b200_device_count", "misa_b200_last_error",
     "misa_b200_create", "misa_b200_destroy", "misa_b200_set_neighbour_offsets", "misa_b200_make_neighbour_offsets",
-    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_plan_push", "misa_b200_plan_stencil", "misa_b200_set_potential",
+    "misa_b200_get_neighbour_offsets", "misa_b200_plan_offsets", "misa_b200_plan_halo", "misa_b200_plan_push", "misa_b200_plan_stencil", "misa_b200_plan_regions", "misa_b200_plan_unit_order", "misa_b200_set_potential",
     "misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc",
     "misa_b200_site_count", "misa_b200_host_register", "misa_b200_host_unregister",
     "misa_b200_upload_atoms", "misa_b200_download_atoms", "misa_b200_upload_inter", "misa_b200_download_inter",
@@ -85,6 +85,8 @@ def load(build=True):
     L.misa_b200_plan_halo.argtypes = [C.POINTER(Domain), i, i, i64p, i64p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(d * 3)]
     L.misa_b200_plan_stencil.argtypes = [C.POINTER(Domain), i, d, i, i64p, C.POINTER(d), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.misa_b200_plan_regions.argtypes = [C.POINTER(Domain), i, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.misa_b200_plan_unit_order.argtypes = [C.POINTER(Domain), i, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.misa_b200_plan_push.argtypes = [C.POINTER(Domain), i64p, i64p, C.POINTER(C.c_int8), C.c_size_t, C.POINTER(C.c_size_t), vp]
     L.misa_b200_set_potential.argtypes = [vp, i, C.POINTER(Table), C.POINTER(Table), C.POINTER(Table)]
     for fn in ("misa_b200_eam_rho_calc", "misa_b200_eam_df_calc", "misa_b200_eam_force_calc"):
@@ -204,6 +206,23 @@ def plan_stencil(dom, parity, cut_lattice=None, crf=None):
                                  r2.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n), C.byref(near), C.byref(half),
                                  prefix.ctypes.data_as(C.POINTER(C.c_int32)), slot.ctypes.data_as(C.POINTER(C.c_int32))))
     return dict(sorted=srt, site_r2=r2, n_near=near.value, n_half=half.value, prefix=prefix, lower_slot=slot[:half.value])
+
+
+def plan_regions(dom, which):
+    """Host-only: (boxes [n][6] = x0,y0,z0,nx,ny,nz in owned-cell coordinates, warp units per parity, interior units)."""
+    L = load()
+    boxes = np.zeros((7, 6), dtype=np.int32)
+    n, units, split = C.c_int32(), C.c_int64(), C.c_int64()
+    _ck(L.misa_b200_plan_regions(C.byref(dom), which, boxes.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(units), C.byref(split)))
+    return boxes[:n.value].copy(), units.value, split.value
+
+
+def plan_unit_order(dom, which, u):
+    """Host-only: (sub-lattice, unit) visited as the u-th warp unit of a launch over plan_regions(dom, which)."""
+    L = load()
+    par, unit = C.c_int32(), C.c_int64()
+    _ck(L.misa_b200_plan_unit_order(C.byref(dom), which, int(u), C.byref(par), C.byref(unit)))
+    return par.value, unit.value
 
 
 def plan_push(dom):

@@ -165,7 +165,7 @@ struct Region { int x0, y0, z0, nx, ny, nz; long long u0; };   // u0: first warp
 struct RegionList { int n; long long units; Region r[EAM_MAX_REGIONS]; long long split; };  // units: warp units per parity
 // split > 0: region 0 is the interior and holds `split` units per parity; the launch then visits BOTH parities' interior units
 // before any boundary unit, so that a warp can wait for the neighbours' ghost push as late as possible (LateWait below)
-__device__ __forceinline__ void unit_split(const RegionList &rl, const long long u, int &par, long long &up) {
+__host__ __device__ __forceinline__ void unit_split(const RegionList &rl, const long long u, int &par, long long &up) {
     if (rl.split <= 0) { par = u >= rl.units; up = u - (par ? rl.units : 0); return; }
     if (u < 2 * rl.split) { par = u >= rl.split; up = u - (par ? rl.split : 0); return; }
     const long long v = u - 2 * rl.split, ub = rl.units - rl.split;

@@ -1199,6 +1199,37 @@ static LevelSel make_levelsel(const misa_b200_ctx *c, const unsigned long long *
     for (int L = 0; L < misa_b200_ctx::kLevels; L++) { ls.n[L] = c->level_n[L]; ls.near_[L] = c->level_near[L]; ls.ofs[L] = (int)c->level_ofs[L]; }
     return ls;
 }
+// host-only view of the work regions (tests): boxes as x0,y0,z0,nx,ny,nz in owned-cell coordinates, split = warp units of
+// the interior box when the launch visits it first (which = 3)
+extern "C" int misa_b200_plan_regions(const misa_b200_domain *dom, int which, int32_t boxes[7][6], int32_t *n_boxes, int64_t *units,
+                                      int64_t *split) {
+    REQ(dom && boxes && n_boxes && which >= 0 && which <= 3, MISA_B200_EINVAL, "misa_b200_plan_regions: bad argument");
+    Geo g;
+    REQ(geo_from_domain(dom, g) == 0, MISA_B200_EINVAL, "misa_b200_plan_regions: bad sub-box sizes");
+    const RegionList rl = make_regions(g, which);
+    *n_boxes = rl.n;
+    for (int b = 0; b < rl.n; b++) {
+        const Region &r = rl.r[b];
+        const int v[6] = {r.x0, r.y0, r.z0, r.nx, r.ny, r.nz};
+        for (int k = 0; k < 6; k++) boxes[b][k] = v[k];
+    }
+    if (units) *units = rl.units;
+    if (split) *split = rl.split;
+    return MISA_B200_OK;
+}
+// host-only: the (sub-lattice, unit) a launch of plan_regions(which) visits as its u-th warp unit -- the kernels' own mapping
+extern "C" int misa_b200_plan_unit_order(const misa_b200_domain *dom, int which, int64_t u, int32_t *parity, int64_t *unit) {
+    REQ(dom && parity && unit && which >= 0 && which <= 3, MISA_B200_EINVAL, "misa_b200_plan_unit_order: bad argument");
+    Geo g;
+    REQ(geo_from_domain(dom, g) == 0, MISA_B200_EINVAL, "misa_b200_plan_unit_order: bad sub-box sizes");
+    const RegionList rl = make_regions(g, which);
+    REQ(u >= 0 && u < 2 * rl.units, MISA_B200_EINVAL, "misa_b200_plan_unit_order: unit out of range");
+    int par;
+    long long up;
+    unit_split(rl, u, par, up);
+    *parity = par; *unit = up;
+    return MISA_B200_OK;
+}
 struct StencilOpt {                 // how one stencil launch deviates from "whole sub-box, host-chosen list, main stream"
     int region = 0;                 // 0 whole, 1 interior, 2 boundary slabs
     const unsigned long long *dmax2 = nullptr;

@@ -219,3 +219,54 @@ def test_stencil_plan_is_a_permutation_with_exact_prefixes(phase, grid, coord):
         vec = [sep2(int(o), pj)[1] for o in pl["sorted"][:half]]
         assert all(v[2] > 0 or (v[2] == 0 and (v[1] > 0 or (v[1] == 0 and v[0] > 0))) for v in vec)
         assert sorted(vec) == sorted(tuple(-c for c in sep2(int(o), pj)[1]) for o in pl["sorted"][half:2 * half])
+
+
+@pytest.mark.parametrize("phase,grid", [((100, 100, 100), (1, 1, 1)), ((80, 8, 8), (2, 1, 1)), ((12, 12, 12), (2, 2, 2)), ((200, 200, 200), (2, 2, 2)),
+                                        ((74, 20, 9), (1, 1, 1))])
+def test_work_regions_partition_the_owned_box(phase, grid):
+    """Every owned cell is computed by exactly one box of a launch; the interior keeps the stencil reach (3 cells) from
+    every face -- and 15 more along x when the neighbours' push is awaited inside the kernel (which = 3)."""
+    dom = capi.make_domain(phase, grid, (0, 0, 0), A, CRF)
+    n = [int(v) for v in dom.sub_box_lattice_size]
+    g = [int(v) for v in dom.lattice_size_ghost]
+
+    def cover(boxes):
+        cnt = np.zeros((n[2], n[1], n[0]), dtype=np.int32)
+        for x0, y0, z0, nx, ny, nz in boxes:
+            assert x0 >= 0 and y0 >= 0 and z0 >= 0 and x0 + nx <= n[0] and y0 + ny <= n[1] and z0 + nz <= n[2]
+            cnt[z0:z0 + nz, y0:y0 + ny, x0:x0 + nx] += 1
+        return cnt
+
+    whole, units, split = capi.plan_regions(dom, 0)
+    assert len(whole) == 1 and split == 0 and np.all(cover(whole) == 1)
+    assert units == (n[0] * n[1] * n[2] + 31) // 32
+    interior, _, _ = capi.plan_regions(dom, 1)
+    slabs, _, _ = capi.plan_regions(dom, 2)
+    if all(n[k] > 2 * g[k] for k in range(3)):
+        assert np.all(cover(list(interior) + list(slabs)) == 1)
+        x0, y0, z0, nx, ny, nz = interior[0]
+        assert (x0, y0, z0) == tuple(g) and (x0 + nx, y0 + ny, z0 + nz) == tuple(n[k] - g[k] for k in range(3))
+    late, units3, split3 = capi.plan_regions(dom, 3)
+    assert np.all(cover(late) == 1)
+    if split3 > 0:
+        x0, y0, z0, nx, ny, nz = late[0]                       # the interior comes first
+        assert split3 == (nx * ny * nz + 31) // 32
+        assert x0 >= g[0] + 15 and x0 + nx <= n[0] - g[0] - 15   # no 128-byte line (16 cells) with a ghost site is read
+        assert y0 >= g[1] and y0 + ny <= n[1] - g[1] and z0 >= g[2] and z0 + nz <= n[2] - g[2]
+    else:
+        assert len(late) == 1
+    assert (split3 > 0) == (n[0] > 2 * (g[0] + 15) and n[1] > 2 * g[1] and n[2] > 2 * g[2])
+
+
+@pytest.mark.parametrize("phase,which", [((40, 9, 8), 3), ((40, 9, 8), 0), ((12, 12, 12), 3), ((12, 12, 12), 2)])
+def test_unit_order_is_a_bijection_with_the_interior_first(phase, which):
+    """The kernels' unit_split: every (sub-lattice, unit) exactly once; with which = 3 no boundary unit comes before the
+    last interior unit of EITHER sub-lattice (that is when a warp starts to wait for the neighbours' push)."""
+    dom = capi.make_domain(phase, (1, 1, 1), (0, 0, 0), A, CRF)
+    _, units, split = capi.plan_regions(dom, which)
+    seen = [capi.plan_unit_order(dom, which, u) for u in range(2 * units)]
+    assert sorted(seen) == [(p, k) for p in range(2) for k in range(units)]
+    if split > 0:
+        assert all(k < split for _, k in seen[:2 * split]) and all(k >= split for _, k in seen[2 * split:])
+    else:
+        assert seen == [(p, k) for p in range(2) for k in range(units)]
