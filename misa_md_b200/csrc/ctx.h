@@ -118,6 +118,7 @@ struct misa_b200_ctx {
     double *d_xyzd = nullptr;             // ONE allocation behind s.x[0..2] and s.df, field stride xyzd_stride doubles
     long long xyzd_stride = 0;
     cudaTextureObject_t tex_all = 0;      // int2 view of the whole block: one handle for all four fields (eam_fast.cuh)
+    cudaTextureObject_t tex_herm = 0;     // int4 view of d_herm (EAM_PHI_TEX experiment only)
     int opt_tex = 1, opt_novac = 1;
     int opt_fast = 1;                     // third-generation kernels (eam_fast.cuh)
     long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant

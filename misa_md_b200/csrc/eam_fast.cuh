@@ -185,7 +185,22 @@ __device__ __noinline__ double3 slow_force_atom(const double *__restrict__ X, co
 }
 
 // one texture handle for x, y, z and df (one allocation, field stride `ns` doubles; ctx.h d_xyzd)
+// EAM_PHI_TEX (experiment, default 0 -- DESIGN.md section 10.1): the single-species force kernel reads the r*phi rows through the
+// TEXTURE path (16-byte texels of the global Hermite block) instead of shared memory, so that the idle TEX pipe takes half
+// of the 64 B of table rows per pair off the load/store path that bounds the kernel.
+#ifndef EAM_PHI_TEX
+#define EAM_PHI_TEX 0
+#endif
+#if EAM_PHI_TEX
+struct TexAll { cudaTextureObject_t t; int ns; cudaTextureObject_t herm; int phi_row0; };
+__device__ __forceinline__ void rows_tex(const cudaTextureObject_t t, const int row, double2 &a, double2 &b) {
+    const int4 u = tex1Dfetch<int4>(t, row), v = tex1Dfetch<int4>(t, row + 1);
+    a = make_double2(__hiloint2double(u.y, u.x), __hiloint2double(u.w, u.z));
+    b = make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
+}
+#else
 struct TexAll { cudaTextureObject_t t; int ns; };
+#endif
 __device__ __forceinline__ double tex_f64(const cudaTextureObject_t t, const int i) {
     const int2 v = tex1Dfetch<int2>(t, i);
     return __hiloint2double(v.y, v.x);
@@ -416,7 +431,11 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
             double z2, z2p, emb;
             double2 r0, r1;
             if (SINGLE) {
+#if EAM_PHI_TEX
+                rows_tex(tex.herm, tex.phi_row0 + sx.m, r0, r1);
+#else
                 rows_s(b_ph0, sx.m, r0, r1);
+#endif
                 z2 = hval(hb, r0, r1);
                 z2p = hder(hs, r0, r1);
                 rows_s(b_el0, sx.m, r0, r1);

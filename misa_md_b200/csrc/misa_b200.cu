@@ -724,6 +724,20 @@ static int build_hermite(misa_b200_ctx *c, const misa_b200_table *elec, const mi
     TRY(dmalloc(&c->d_herm, h.size() / 2));
     CU(cudaMemcpy(c->d_herm, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     c->hermite_ok = ok;
+#if EAM_PHI_TEX
+    {
+        if (c->tex_herm) { cudaDestroyTextureObject(c->tex_herm); c->tex_herm = 0; }
+        cudaResourceDesc rd;
+        cudaTextureDesc td;
+        memset(&rd, 0, sizeof rd); memset(&td, 0, sizeof td);
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = c->d_herm;
+        rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindSigned);
+        rd.res.linear.sizeInBytes = h.size() * sizeof(double);
+        td.readMode = cudaReadModeElementType;
+        CU(cudaCreateTextureObject(&c->tex_herm, &rd, &td, nullptr));
+    }
+#endif
     return 0;
 }
 
@@ -1463,7 +1477,12 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     }
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
+#if EAM_PHI_TEX
+        const TexAll tex = {c->tex_all, (int)c->xyzd_stride, c->tex_herm,
+                            (c->tab.n_types + sp.staged_id[0] * c->tab.n_types + sp.staged_id[0]) * (c->tab.n_r + 1)};
+#else
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+#endif
         const RegionList rl = make_regions(g, late ? 3 : so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         const MinorList ml = minor_list(c);
@@ -1483,7 +1502,12 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
+#if EAM_PHI_TEX
+        const int phi_row0 = single ? (c->tab.n_types + sp.single * c->tab.n_types + sp.single) * (c->tab.n_r + 1) : 0;
+        const TexAll tex = {c->tex_all, (int)c->xyzd_stride, c->tex_herm, phi_row0};
+#else
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+#endif
         const RegionList rl = make_regions(g, late ? 3 : so.region);
         const LevelSel ls = make_levelsel(c, so.dmax2);
         if (rl.units == 0) return 0;

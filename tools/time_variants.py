@@ -18,7 +18,9 @@ ctx.prepare()
 ctx.step(200)
 ms = ctx.timed_steps(50)
 ctx.profile_enable(True); ctx.step(20); pr = ctx.profile_read(); ctx.profile_enable(False)
-print("%%-28s %%.4f ms/step | rho %%.4f force %%.4f" %% (os.path.basename(os.environ.get("MISA_B200_LIB", "default")), ms / 50, pr["rho"][0] / pr["rho"][1], pr["force"][0] / pr["force"][1]), flush=True)
+import numpy as np
+a = ctx.download()
+print("%%-28s %%.4f ms/step | rho %%.4f force %%.4f | checksums f %%.17g x %%.17g" %% (os.path.basename(os.environ.get("MISA_B200_LIB", "default")), ms / 50, pr["rho"][0] / pr["rho"][1], pr["force"][0] / pr["force"][1], float(np.abs(a["f"]).sum()), float(np.abs(a["x"]).sum())), flush=True)
 ''' % here
 for lib in [None] + sys.argv[1:]:
     env = dict(os.environ)
