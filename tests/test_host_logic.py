@@ -133,7 +133,8 @@ def test_sub_box_state_matches_reference_builder_rule():
     assert np.array_equal(own["v"], loc["v"])
 
 
-@pytest.mark.parametrize("phase,grid", [((12, 12, 12), (2, 2, 2)), ((12, 8, 10), (2, 1, 1)), ((8, 16, 18), (1, 2, 3)), ((8, 9, 10), (1, 1, 1))])
+@pytest.mark.parametrize("phase,grid", [((12, 12, 12), (2, 2, 2)), ((12, 8, 10), (2, 1, 1)), ((8, 16, 18), (1, 2, 3)), ((8, 9, 10), (1, 1, 1)),
+                                        ((12, 3, 8), (4, 1, 2)), ((9, 12, 5), (3, 4, 1)), ((6, 6, 6), (2, 2, 2))])   # incl. sub-boxes as narrow as the ghost shell
 def test_direct_push_map_equals_the_staged_exchange(phase, grid, pot):
     """misa_b200_plan_push (what csrc/p2p.cuh applies with one kernel over NVLink peer memory) against the reference's
     three staged exchanges run by the oracle on every sub-box: same ghost positions (bits) and types everywhere."""
