@@ -33,7 +33,21 @@ static void check(int rc, const char *what) {
     }
 }
 
-void cuda_env_init() { check(misa_b200_env_init(-1), "cuda_env_init"); } // device = LOCAL_RANK (one rank <-> one GPU)
+// One MPI rank <-> one GPU: the device is this rank's index among the ranks of its NODE (shared-memory split of
+// MPI_COMM_WORLD), modulo the visible devices -- works under mpirun / srun / torchrun alike, no launcher variable needed.
+void cuda_env_init() {
+    int local = -1, inited = 0;
+    MPI_Initialized(&inited);
+    if (inited) {
+        MPI_Comm node;
+        if (MPI_Comm_split_type(MPI_COMM_WORLD, MPI_COMM_TYPE_SHARED, 0, MPI_INFO_NULL, &node) == MPI_SUCCESS) {
+            MPI_Comm_rank(node, &local);
+            MPI_Comm_free(&node);
+        }
+    }
+    const int n = misa_b200_device_count();
+    check(misa_b200_env_init(local >= 0 && n > 0 ? local % n : -1), "cuda_env_init");
+}
 
 void cuda_env_clean() {
     if (g_registered) { misa_b200_host_unregister(g_registered); g_registered = nullptr; }

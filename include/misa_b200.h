@@ -233,6 +233,11 @@ int misa_b200_profile_read(misa_b200_ctx *ctx, double ms_sum[MISA_B200_K_COUNT],
 int misa_b200_launch_count(misa_b200_ctx *ctx, int64_t *n); /* kernels launched since create */
 /* device time of n_steps through CUDA events on the context's stream (ms) */
 int misa_b200_timed_steps(misa_b200_ctx *ctx, int n_steps, double *ms);
+/* what the stencil kernels loop on the CURRENT resident state (diagnostic launch, not on the step path): out[0] owned sites,
+ * [1] offsets looped (per-warp prefixes of the pruned list), [2] pair evaluations executed (branch-free near group + voted
+ * far offsets), [3] pairs inside the cutoff -- totals over the sub-box; divide by out[0] for per-atom figures. Feeds the
+ * fp64 view of bench.py's roofline ("report both N_off and N_pair actually used"). */
+int misa_b200_stencil_stats(misa_b200_ctx *ctx, double out[4]);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ EXPORTS = [
     "misa_b200_pass_force", "misa_b200_pass_verlet1", "misa_b200_pass_verlet2", "misa_b200_set_option", "misa_b200_query",
     "misa_b200_comm_unique_id", "misa_b200_comm_init", "misa_b200_comm_destroy",
     "misa_b200_profile_enable", "misa_b200_profile_read", "misa_b200_launch_count", "misa_b200_timed_steps",
-    "misa_b200_build_world", "misa_b200_temperature", "misa_b200_rescale_to", "misa_b200_dump_records",
+    "misa_b200_stencil_stats", "misa_b200_build_world", "misa_b200_temperature", "misa_b200_rescale_to", "misa_b200_dump_records",
 ]
 
 
@@ -118,6 +118,7 @@ def load(build=True):
     L.misa_b200_profile_read.argtypes = [vp, C.POINTER(d * K_COUNT), C.POINTER(C.c_int64 * K_COUNT)]
     L.misa_b200_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     L.misa_b200_timed_steps.argtypes = [vp, i, C.POINTER(d)]
+    L.misa_b200_stencil_stats.argtypes = [vp, C.POINTER(d * 4)]
     L.misa_b200_build_world.argtypes = [vp, C.c_uint32, d, C.POINTER(C.c_int32 * 3), C.c_uint64]
     L.misa_b200_temperature.argtypes = [vp, C.c_uint64, C.POINTER(d * 4)]
     L.misa_b200_rescale_to.argtypes = [vp, d, C.c_uint64]
@@ -431,6 +432,13 @@ class Context:
         n = (C.c_int64 * K_COUNT)()
         _ck(self.L.misa_b200_profile_read(self.h, C.byref(ms), C.byref(n)))
         return {K_NAMES[k]: (ms[k], n[k]) for k in range(K_COUNT)}
+
+    def stencil_stats(self):
+        """Per owned site: offsets looped, pair evaluations executed, pairs inside the cutoff (current state)."""
+        out = (C.c_double * 4)()
+        _ck(self.L.misa_b200_stencil_stats(self.h, C.byref(out)))
+        n = max(out[0], 1.0)
+        return dict(sites=int(out[0]), offsets_per_atom=out[1] / n, evals_per_atom=out[2] / n, pairs_per_atom=out[3] / n)
 
     def launch_count(self):
         n = C.c_int64()

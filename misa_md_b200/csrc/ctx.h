@@ -71,6 +71,7 @@ struct P2pPeers {
     double shift[27][3];           // periodic image shift of the group
     long long stride;              // field stride of the block (doubles)
     unsigned int mask;             // direction codes in use
+    long long spin_limit;          // SM clocks a flag wait may take before it gives up with an error
 };
 
 struct misa_b200_ctx {
@@ -154,6 +155,9 @@ struct misa_b200_ctx {
     int opt_late = 1;                     // wait for the neighbours' push inside the stencil kernels (interior units first)
     int opt_p2p = -1;                     // -1 / 1: whenever every surrounding sub-box is peer-mapped on this node; 0: NCCL send/recv
     bool p2p_active = false;
+    int opt_p2p_timeout_s = 30;           // flag waits give up after this many seconds (error, no stores; p2p.cuh)
+    unsigned int p2p_last_error = 0;      // flag code of the last timeout reported
+    bool p2p_fault = false;               // a wait timed out and the caller has been told: the push stays off until comm_init re-synchronises
     int n_push = 0;
     int *d_push_dst = nullptr, *d_push_src = nullptr;
     int8_t *d_push_code = nullptr;

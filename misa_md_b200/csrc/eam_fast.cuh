@@ -694,3 +694,41 @@ EAM_UNROLL(2)
         if (lane == 0) { s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz; }
     }
 }
+
+// ---- diagnostics for the fp64 view of the roofline (bench.py, not on the step path): what the stencil kernels LOOP on the
+//      current state -- offsets per atom (the per-warp prefix), pair evaluations per atom (branch-free near group + the far
+//      offsets a warp-wide vote lets through) and pairs actually inside the cutoff. Same list_len / vote logic as k_force_f.
+//      out[0] lanes (live atoms), [1] offsets looped, [2] pair evaluations, [3] pairs in range -----------------------------
+__global__ void __launch_bounds__(256)
+k_stencil_stats(const Geo g, const Soa s, const int *__restrict__ offs, const int n_list, const int n_near, const RegionList rl, const LevelSel ls,
+                unsigned long long *__restrict__ out) {
+    const int lg = base_level(ls);
+    const bool hot_ok = hot_map_usable(ls);
+    const int lane = threadIdx.x & 31;
+    unsigned long long lanes = 0, looped = 0, evals = 0, inr = 0;
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < 2 * rl.units; u += ((long long)gridDim.x * blockDim.x) >> 5) {
+        int par;
+        long long up;
+        unit_split(rl, u, par, up);
+        const int d0 = region_unit_to_dev(g, rl, up, par, lane);
+        const bool live = d0 >= 0;
+        const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);
+        const int *off = offs + (par ? n_list : 0);
+        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
+                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
+        for (int q = 0; q < n_off; q++) {
+            const int j = d + off[q];
+            const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+            const bool in = s.type[j] >= 0 && fma(dz, dz, fma(dy, dy, dx * dx)) < g.rc2;
+            const bool ev = q < n_near || __any_sync(0xffffffffu, in);
+            if (live) { looped++; evals += ev; inr += in && s.type[d] >= 0; }
+        }
+        lanes += live;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lanes += __shfl_xor_sync(0xffffffffu, lanes, o); looped += __shfl_xor_sync(0xffffffffu, looped, o);
+        evals += __shfl_xor_sync(0xffffffffu, evals, o); inr += __shfl_xor_sync(0xffffffffu, inr, o);
+    }
+    if (lane == 0) { atomicAdd(out, lanes); atomicAdd(out + 1, looped); atomicAdd(out + 2, evals); atomicAdd(out + 3, inr); }
+}

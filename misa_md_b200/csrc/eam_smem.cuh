@@ -175,7 +175,7 @@ __host__ __device__ __forceinline__ void unit_split(const RegionList &rl, const 
 // Ghost push of p2p.cuh consumed INSIDE the stencil kernel: interior units read no ghost site (nor any 32-byte sector that
 // holds one), so they run while the neighbours' stores are still in flight; the first boundary unit of a warp spins on the
 // arrive flags (ld.acquire.sys). The L1 / texture cache is cold for every sector with a ghost in it until then.
-struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; };
+struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; long long limit; };
 __device__ __forceinline__ void late_wait(const LateWait &lw, const int lane) {
     if (lane < 27 && ((lw.mask >> lane) & 1u)) {
         const unsigned long long *w = lw.flags + 32 + lane;   // P2P_ARRIVE + code
@@ -183,7 +183,7 @@ __device__ __forceinline__ void late_wait(const LateWait &lw, const int lane) {
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
-            if (v < lw.epoch && clock64() - t0 > 6000000000LL) { *(volatile unsigned int *)lw.err = 200u + lane; break; }
+            if (v < lw.epoch && clock64() - t0 > lw.limit) { *(volatile unsigned int *)lw.err = 200u + lane; break; }
         } while (v < lw.epoch);
     }
     __syncwarp();

@@ -17,6 +17,7 @@
 #include "nccl_dl.cuh"
 #include "inter.cuh"
 #include "eam_smem.cuh"
+#include "eam_fast.cuh"
 #include "eam_sym.cuh"
 #include "dump.cuh"
 #include "world.cuh"
@@ -41,8 +42,13 @@ extern "C" int misa_b200_env_init(int device) {
     int n = misa_b200_device_count();
     REQ(n > 0, MISA_B200_ENODEV, "misa_b200_env_init: no CUDA device visible (there is no CPU fallback)");
     if (device < 0) {
-        const char *lr = getenv("LOCAL_RANK");
-        device = lr ? atoi(lr) % n : 0;
+        // node-local rank as the launcher exports it: torchrun, Open MPI, MVAPICH2, Slurm, PMI (Intel MPI / MPICH hydra);
+        // the hook shim passes MPI_Comm_split_type(MPI_COMM_TYPE_SHARED)'s rank explicitly when none of them is set
+        static const char *const names[] = {"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID",
+                                            "MPI_LOCALRANKID", "PMI_LOCAL_RANK"};
+        device = 0;
+        for (const char *nm : names)
+            if (const char *lr = getenv(nm)) { device = atoi(lr) % n; break; }
     }
     REQ(device < n, MISA_B200_EINVAL, "misa_b200_env_init: device index out of range");
     CU(cudaSetDevice(device));
@@ -840,11 +846,24 @@ extern "C" int misa_b200_download_atoms(misa_b200_ctx *c, void *atoms) {
     return d2h_aos(c, atoms, F_ALL, 0);
 }
 
+// A flag wait of the ghost push timed out (p2p.cuh): tell the caller ONCE, clear the word, and keep the push path off --
+// the epochs of the sub-boxes no longer agree -- until misa_b200_comm_init re-synchronises them.
+static int p2p_check(misa_b200_ctx *c) {
+    if (c->h_p2p_err && *c->h_p2p_err != 0) {
+        const unsigned int what = *c->h_p2p_err;
+        *c->h_p2p_err = 0;
+        c->p2p_fault = true;
+        c->p2p_last_error = what;
+        return fail(MISA_B200_ENCCL, "ghost push over peer memory: a neighbouring sub-box did not answer within " + std::to_string(c->opt_p2p_timeout_s) +
+                                         " s (flag " + std::to_string(what) + "); nothing was stored into its ghosts. Call misa_b200_comm_init again to re-synchronise");
+    }
+    REQ(!c->p2p_fault, MISA_B200_ESTATE, "ghost push timed out earlier: call misa_b200_comm_init again before stepping");
+    return 0;
+}
 extern "C" int misa_b200_sync(misa_b200_ctx *c) {
     REQ(c, MISA_B200_EINVAL, "null ctx");
     CU(cudaStreamSynchronize(c->stream));
-    REQ(!c->h_p2p_err || *c->h_p2p_err == 0, MISA_B200_ENCCL, "ghost push over peer memory: a neighbouring sub-box did not answer within the spin limit");
-    return 0;
+    return p2p_check(c);
 }
 
 extern "C" int misa_b200_set_timestep(misa_b200_ctx *c, double dt) {
@@ -870,6 +889,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "p2p")) c->opt_p2p = value;
     else if (!strcmp(name, "mark")) c->opt_mark = value;
     else if (!strcmp(name, "late")) c->opt_late = value;
+    else if (!strcmp(name, "p2p_timeout_s")) { c->opt_p2p_timeout_s = std::max(1, value); c->p2p.spin_limit = (long long)c->opt_p2p_timeout_s * 2000000000LL; }
     else if (!strcmp(name, "minor_staged")) c->opt_minor_staged = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
@@ -908,7 +928,7 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
         *value = (double)n;
     }
     else if (!strcmp(name, "mark_level")) *value = c->mark_valid ? c->mark_T_used : -1;
-    else if (!strcmp(name, "p2p_error")) *value = c->h_p2p_err ? (double)*c->h_p2p_err : 0.0;
+    else if (!strcmp(name, "p2p_error")) *value = c->h_p2p_err && *c->h_p2p_err ? (double)*c->h_p2p_err : (double)c->p2p_last_error;
     else if (!strcmp(name, "sym")) *value = planned && sym_active(c, sp) ? 1 : 0;
     else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
     return 0;
@@ -1268,7 +1288,7 @@ static bool late_wait_ok(const misa_b200_ctx *c, const StagePlan &sp, bool plann
 }
 static LateWait make_latewait(const misa_b200_ctx *c) {
     LateWait lw;
-    lw.flags = c->d_flags; lw.epoch = c->p2p_epoch; lw.mask = c->p2p.mask; lw.err = c->d_p2p_err;
+    lw.flags = c->d_flags; lw.epoch = c->p2p_epoch; lw.mask = c->p2p.mask; lw.err = c->d_p2p_err; lw.limit = c->p2p.spin_limit;
     return lw;
 }
 
@@ -1782,7 +1802,7 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
         TRY(launch_force(c, false, boundary));
     }
     CU(cudaEventSynchronize(c->ev_act));
-    REQ(!c->h_p2p_err || *c->h_p2p_err == 0, MISA_B200_ENCCL, "ghost push over peer memory: a neighbouring sub-box did not answer within the spin limit");
+    TRY(p2p_check(c));
     c->inter_active = c->h_stepinfo[0] > 0;
     c->pipe_steps++;
     if (c->inter_active || c->h_counters[3] != 0) {
@@ -1863,6 +1883,26 @@ extern "C" int misa_b200_timed_steps(misa_b200_ctx *c, int n_steps, double *ms) 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms = f;
     return rc;
+}
+
+extern "C" int misa_b200_stencil_stats(misa_b200_ctx *c, double out[4]) {
+    TRY(ready(c));
+    REQ(out, MISA_B200_EINVAL, "null argument");
+    unsigned long long *d = nullptr, h[4] = {0, 0, 0, 0};
+    TRY(dmalloc(&d, 4));
+    CU(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), c->stream));
+    const RegionList rl = make_regions(c->geo, 0);
+    // the word the sync-free step's kernels read: the global maximum displacement of the last k_verlet1 (host level otherwise)
+    const LevelSel ls = make_levelsel(c, pipe_ok(c) && c->pipe_steps > 0 ? c->d_stepinfo_g + 1 : nullptr);
+    k_stencil_stats<<<std::max(1, c->sm_count) * 8, 256, 0, c->stream>>>(c->geo, c->s, c->d_off_full, c->n_full, c->near_full, rl, ls, d);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CU(e);
+    for (int k = 0; k < 4; k++) out[k] = (double)h[k];
+    return 0;
 }
 
 // atom::setv, reference src/atom.cpp:475-494

@@ -23,7 +23,10 @@
 #define P2P_READY 0
 #define P2P_ARRIVE 32
 #define P2P_FLAG_WORDS 64
-#define P2P_SPIN_LIMIT (6000000000LL)   // ~3 s of SM clocks: a peer that never answers ends the wait with an error, not a hang
+// A peer that never answers ends the wait with an error, not a hang: P2pPeers::spin_limit SM clocks (default 30 s; option
+// "p2p_timeout_s" / MISA_B200_OPTS). A push kernel whose wait for READY timed out stores NOTHING into the neighbours'
+// ghosts and does not signal ARRIVE -- the neighbour may still be reading them -- so rank skew beyond the limit is an
+// error on every rank concerned, never a data race.
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -36,10 +39,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 // code k = (sx+1) + 3 (sy+1) + 9 (sz+1): the ORIGIN of my ghosts with that code sits at sub-box offset +s from me; I push my
 // own group k to the sub-box at offset -s. Thread k handles direction k.
-__device__ __forceinline__ void p2p_wait(const unsigned long long *w, const unsigned long long epoch, unsigned int *err, const unsigned what) {
+__device__ __forceinline__ bool p2p_wait(const unsigned long long *w, const unsigned long long epoch, unsigned int *err, const unsigned what,
+                                         const long long limit) {
     const long long t0 = clock64();
     while (ld_acquire_sys(w) < epoch)
-        if (clock64() - t0 > P2P_SPIN_LIMIT) { *(volatile unsigned int *)err = what; break; }
+        if (clock64() - t0 > limit) { *(volatile unsigned int *)err = what; return false; }
+    return true;
 }
 // READY: I am receiver for code k -> tell its origin, which is my destination for code 26 - k, that everything enqueued
 // before this kernel (the readers of my ghosts) is done. `epoch` may lie ahead: "free up to and including exchange epoch".
@@ -54,15 +59,20 @@ __global__ void k_p2p_wait_arrive(const P2pPeers pp, const unsigned long long ep
                                   unsigned int *__restrict__ err) {
     const int k = threadIdx.x;
     if (k >= 27 || !((pp.mask >> k) & 1u)) return;
-    p2p_wait(my_flags + P2P_ARRIVE + k, epoch, err, 100u + k);
+    p2p_wait(my_flags + P2P_ARRIVE + k, epoch, err, 100u + k, pp.spin_limit);
 }
 // head of a push kernel: every destination has freed its ghosts; tail: the LAST CTA to finish tells every destination
-__device__ __forceinline__ void p2p_push_head(const P2pPeers &pp, const unsigned long long epoch, const unsigned long long *my_flags, unsigned int *err) {
+// returns false (for the whole CTA) when a destination never freed its ghosts: the caller must not store into them
+__device__ __forceinline__ bool p2p_push_head(const P2pPeers &pp, const unsigned long long epoch, const unsigned long long *my_flags, unsigned int *err) {
+    __shared__ int timed_out;
     const int k = threadIdx.x;
-    if (k < 27 && ((pp.mask >> k) & 1u)) p2p_wait(my_flags + P2P_READY + k, epoch, err, 1u + k);
+    if (k == 0) timed_out = 0;
     __syncthreads();
+    if (k < 27 && ((pp.mask >> k) & 1u) && !p2p_wait(my_flags + P2P_READY + k, epoch, err, 1u + k, pp.spin_limit)) timed_out = 1;
+    __syncthreads();
+    return timed_out == 0;
 }
-__device__ __forceinline__ void p2p_push_tail(const P2pPeers &pp, const unsigned long long epoch, unsigned int *done) {
+__device__ __forceinline__ void p2p_push_tail(const P2pPeers &pp, const unsigned long long epoch, unsigned int *done, const unsigned int *err) {
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -74,15 +84,16 @@ __device__ __forceinline__ void p2p_push_tail(const P2pPeers &pp, const unsigned
     const int k = threadIdx.x;
     if (k == 0) *done = 0;                           // next exchange (stream-ordered after this kernel)
     __threadfence_system();
+    if (*(volatile const unsigned int *)err != 0) return;   // some CTA gave up on READY: its part was not stored, nothing ARRIVEd
     if (k < 27 && ((pp.mask >> k) & 1u)) st_release_sys(pp.flags[k] + P2P_ARRIVE + k, epoch);
 }
 
 __global__ void __launch_bounds__(MISA_BLOCK)
 k_p2p_push_x(const P2pPeers pp, const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code, const Soa s,
              const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err) {
-    p2p_push_head(pp, epoch, my_flags, err);
+    const bool ok = p2p_push_head(pp, epoch, my_flags, err);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
+    if (ok && i < n) {
         const int a = src[i], b = dst[i], k = code[i];
         double x = s.x[0][a], y = s.x[1][a], z = s.x[2][a];
         if (pp.shift[k][0] != 0.0) x = __dadd_rn(x, pp.shift[k][0]);
@@ -92,15 +103,15 @@ k_p2p_push_x(const P2pPeers pp, const int n, const int *__restrict__ dst, const 
         P[b] = x; P[pp.stride + b] = y; P[2 * pp.stride + b] = z;
         pp.type[k][b] = s.type[a];
     }
-    p2p_push_tail(pp, epoch, done);
+    p2p_push_tail(pp, epoch, done, err);
 }
 __global__ void __launch_bounds__(MISA_BLOCK)
 k_p2p_push_df(const P2pPeers pp, const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code, const Soa s,
               const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err) {
-    p2p_push_head(pp, epoch, my_flags, err);
+    const bool ok = p2p_push_head(pp, epoch, my_flags, err);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pp.xyzd[code[i]][3 * pp.stride + dst[i]] = s.df[src[i]];
-    p2p_push_tail(pp, epoch, done);
+    if (ok && i < n) pp.xyzd[code[i]][3 * pp.stride + dst[i]] = s.df[src[i]];
+    p2p_push_tail(pp, epoch, done, err);
 }
 
 // ---- set-up: exchange IPC handles of the position/df block, the type array and the flag words over the NCCL
@@ -162,6 +173,11 @@ static int p2p_setup(misa_b200_ctx *c) {
     P2pPeers &pp = c->p2p;
     memset(&pp, 0, sizeof pp);
     pp.stride = c->xyzd_stride;
+    pp.spin_limit = (long long)c->opt_p2p_timeout_s * 2000000000LL;
+    // a fresh set-up re-synchronises everything a timed-out exchange left behind: epochs restart at 0 on every rank
+    CU(cudaMemsetAsync(c->d_flags, 0, P2P_FLAG_WORDS * sizeof(unsigned long long), c->stream));
+    *c->h_p2p_err = 0;
+    c->p2p_fault = false;
     std::vector<void *> mapped_xyzd(n, nullptr), mapped_type(n, nullptr), mapped_flags(n, nullptr);
     mapped_xyzd[me] = c->d_xyzd; mapped_type[me] = c->s.type; mapped_flags[me] = c->d_flags;
     for (int r = 0; r < n; r++) {

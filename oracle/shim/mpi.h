@@ -21,7 +21,15 @@ typedef int MPI_Info;
 #define MPI_INFO_NULL 0
 #define MPI_MODE_CREATE 1
 #define MPI_MODE_WRONLY 4
+#define MPI_SUCCESS 0
+#define MPI_COMM_TYPE_SHARED 1
 extern "C" {
+// the accelerator hook shim (arch_cuda/cuda_hooks.cpp) asks for its node-local rank; the stand-in says "MPI not initialised"
+// (ranks are threads of one process here), which sends the shim to the launcher's environment variables
+int MPI_Initialized(int *flag);
+int MPI_Comm_split_type(MPI_Comm comm, int split_type, int key, MPI_Info info, MPI_Comm *newcomm);
+int MPI_Comm_rank(MPI_Comm comm, int *rank);
+int MPI_Comm_free(MPI_Comm *comm);
 double MPI_Wtime();
 int MPI_Abort(MPI_Comm comm, int code);
 int MPI_Allreduce(const void *send, void *recv, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
