@@ -85,7 +85,19 @@ __device__ __forceinline__ double hder(const HSlope &g, const double2 r0, const 
 
 // rows (m, m+1): shared-space loads for the single-species path, generic loads (shared or global window,
 // resolved per lane by the hardware) for the multi-species path
-__device__ __forceinline__ void rows_s(const uint32_t base, const int m, double2 &a, double2 &b) {
+// EAM_EXP_NOCONFLICT (measurement only, WRONG RESULTS, default 0): the low three bits of the row index are replaced by the
+// lane's, so that the eight lanes of every quarter-warp hit eight different 16-byte bank groups -- the conflict-free
+// shared-memory gather no exact layout can deliver for random rows. Its time is the ceiling of every table-layout trick
+// (DESIGN.md section 10.1).
+#ifndef EAM_EXP_NOCONFLICT
+#define EAM_EXP_NOCONFLICT 0
+#endif
+__device__ __forceinline__ void rows_s(const uint32_t base, const int m_, double2 &a, double2 &b) {
+#if EAM_EXP_NOCONFLICT
+    const int m = (m_ & ~7) | (int)(threadIdx.x & 7u);
+#else
+    const int m = m_;
+#endif
     const uint32_t addr = base + ((uint32_t)m << 4);
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a.x), "=d"(a.y) : "r"(addr));
     asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(b.x), "=d"(b.y) : "r"(addr));

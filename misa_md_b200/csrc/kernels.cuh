@@ -182,7 +182,11 @@ k_force(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ of
 //      bit-exact. Run-aways are appended to `runaway_sites` (device indices); the site is vacated by
 //      k_decide_vacate after the list has been sorted into the reference's k,j,i order. ------------------
 #define MARK_CAP 4096     // marking atoms per step; beyond it the map is void (stepinfo[2] tells the stencil kernels)
-struct VerletPar { double dt; double c[MISA_MAX_TYPES]; int mark_T; unsigned char *hot; unsigned char epoch; unsigned long long *mark_count; };
+struct VerletPar { double dt; double c[MISA_MAX_TYPES]; int mark_T; unsigned char *hot; unsigned char epoch; unsigned long long *mark_count;
+                   float inv100_a, lev_slack; };   // 100 / a and 2e-4 / a, both rounded up (disp_level_fast)
+// dt / (2 m) of species t WITHOUT indexing the kernel parameter dynamically: `vp.c[t]` made the compiler copy the whole
+// parameter struct to local memory in every thread (9 STL + 1 LDL per atom in the SASS of the round-1 kernels)
+__device__ __forceinline__ double kick_coef(const VerletPar &vp, const int t) { return t == 0 ? vp.c[0] : (t == 1 ? vp.c[1] : vp.c[2]); }
 // max over the warp, then one atomicMax on the bit pattern (non-negative doubles order like unsigned integers)
 __device__ __forceinline__ void report_max(double v, unsigned long long *__restrict__ out) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -198,6 +202,15 @@ __device__ __forceinline__ unsigned char disp_level(const double dist2, const do
     const double l = ceil(fma(sqrt(dist2), inv, 2e-6 * inv));    // 2e-6 A of slack: never below the host's ceil((d + 1e-6) / (0.01 a))
     return (unsigned char)(l > 255.0 ? 255 : (int)l);
 }
+// The same level without the fp64 square root (k_verlet1 is a streaming kernel: DSQRT + ceil + the conversions were a third of
+// its instructions): single-precision sqrt of the squared displacement, scaled with every rounding pushed UPWARDS -- the level
+// is a bound, so "one too high" (probability ~1e-5 per atom, at a level boundary) is safe, "one too low" never happens:
+// sqrtf and the conversion err by < 2^-23 relative each, the factor 1 + 2^-20 covers both with room, the slack is the host's.
+__device__ __forceinline__ unsigned char disp_level_fast(const double dist2, const float inv100_a, const float slack) {
+    const float r = __fsqrt_ru(__double2float_ru(dist2));
+    const float l = ceilf(__fmaf_ru(r * 1.00000095f, inv100_a, slack));
+    return (unsigned char)(l > 255.0f ? 255 : (int)l);
+}
 // squared displacement of the atom from its ideal site after the drift (0 for vacant sites).
 // KICK2: the second half-kick of the step that just finished (NewtonMotion::secondstep, same f) is applied first --
 // inside a multi-step call the two streaming passes over v and f become one (bit-identical: the same two rounded adds)
@@ -209,18 +222,21 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
     const int t = s.type[d];
     if (t < 0) { s.ulev[d] = 0; return 0.0; }
 
-    const double cm = vp.c[t];
-    double x[3];
+    // all nine loads first (the Soa pointers carry no restrict: interleaved with the stores they were issued in three
+    // dependent rounds, and the kernel sat at half of the HBM bandwidth)
+    double f[3], v[3], x[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { f[k] = __ldg(s.f[k] + d); v[k] = s.v[k][d]; x[k] = s.x[k][d]; }
+    const double cm = kick_coef(vp, t);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const double kick = __dmul_rn(cm, s.f[k][d]);
-        double v = s.v[k][d];
-        if (KICK2) v = __dadd_rn(v, kick);
-        v = __dadd_rn(v, kick);
-        s.v[k][d] = v;
-        x[k] = __dadd_rn(s.x[k][d], __dmul_rn(vp.dt, v));
-        s.x[k][d] = x[k];
+        const double kick = __dmul_rn(cm, f[k]);
+        if (KICK2) v[k] = __dadd_rn(v[k], kick);
+        v[k] = __dadd_rn(v[k], kick);
+        x[k] = __dadd_rn(x[k], __dmul_rn(vp.dt, v[k]));
     }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { s.v[k][d] = v[k]; s.x[k][d] = x[k]; }
     // ideal site, reference src/atom.cpp:34-38: i is the doubled-x sub-box index
     const long long i = 2LL * cx + p;
     const double xt = __dmul_rn(__dmul_rn((double)(i + 2LL * g.lo[0]), 0.5), g.a);
@@ -235,7 +251,7 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
         if (slot < runaway_cap) runaway_sites[slot] = d;
         else atomicExch(&counters[3], 1);
     }
-    const int lev = disp_level(dist, g.a);
+    const int lev = disp_level_fast(dist, vp.inv100_a, vp.lev_slack);
     s.ulev[d] = (unsigned char)lev;
     // (a plain look first: once the cap is passed -- thermalisation transients, when most atoms lie above T -- nobody queues on
     // the counter any more; it then stands above MARK_CAP, which is what tells the stencil kernels to ignore the map)
@@ -274,9 +290,12 @@ k_verlet2(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
     const int d = owned_cell_to_dev(g, p, c, cx, y, z);
     const int t = s.type[d];
     if (t < 0) return;
-    const double cm = vp.c[t];
+    const double cm = kick_coef(vp, t);
+    double f[3], v[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) s.v[k][d] = __dadd_rn(s.v[k][d], __dmul_rn(cm, s.f[k][d]));
+    for (int k = 0; k < 3; k++) { f[k] = __ldg(s.f[k] + d); v[k] = s.v[k][d]; }   // loads first (no restrict on the Soa pointers)
+#pragma unroll
+    for (int k = 0; k < 3; k++) s.v[k][d] = __dadd_rn(v[k], __dmul_rn(cm, f[k]));
 }
 
 // ---- K6 halo: LatPacker / DfEmbedPacker (reference src/pack/lat_particle_packer.cpp:153-193,

@@ -1593,6 +1593,9 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
     vp.dt = c->dt;
     for (int i = 0; i < MISA_MAX_TYPES; i++) vp.c[i] = c->dt_inv_m[i];
     vp.mark_T = 0; vp.hot = nullptr; vp.epoch = 0; vp.mark_count = nullptr;
+    // level arithmetic of k_verlet1 in single precision, every constant rounded UP (kernels.cuh:disp_level_fast)
+    vp.inv100_a = nextafterf((float)(100.0 / c->geo.a), INFINITY);
+    vp.lev_slack = nextafterf((float)(2e-4 / c->geo.a), INFINITY);
     return vp;
 }
 

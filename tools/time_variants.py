@@ -20,7 +20,9 @@ ms = ctx.timed_steps(50)
 ctx.profile_enable(True); ctx.step(20); pr = ctx.profile_read(); ctx.profile_enable(False)
 import numpy as np
 a = ctx.download()
-print("%%-28s %%.4f ms/step | rho %%.4f force %%.4f | checksums f %%.17g x %%.17g" %% (os.path.basename(os.environ.get("MISA_B200_LIB", "default")), ms / 50, pr["rho"][0] / pr["rho"][1], pr["force"][0] / pr["force"][1], float(np.abs(a["f"]).sum()), float(np.abs(a["x"]).sum())), flush=True)
+sl = lambda k: pr[k][0] / max(pr[k][1], 1)
+ctx.step(1); ctx.profile_enable(True); [ctx.step(1) for _ in range(10)]; p1 = ctx.profile_read(); ctx.profile_enable(False)   # single-step calls: k_verlet2 runs
+print("%%-28s %%.4f ms/step | rho %%.4f force %%.4f verlet1 %%.4f halo_x %%.4f halo_df %%.4f verlet2(1-step calls) %%.4f | checksums f %%.17g x %%.17g" %% (os.path.basename(os.environ.get("MISA_B200_LIB", "default")), ms / 50, sl("rho"), sl("force"), sl("verlet1"), sl("halo_x"), sl("halo_df"), p1["verlet2"][0] / max(p1["verlet2"][1], 1), float(np.abs(a["f"]).sum()), float(np.abs(a["x"]).sum())), flush=True)
 ''' % here
 for lib in [None] + sys.argv[1:]:
     env = dict(os.environ)
