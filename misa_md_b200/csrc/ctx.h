@@ -173,7 +173,9 @@ struct misa_b200_ctx {
     InterSoa inter{};
     int inter_cap = 0;
     int *d_counters = nullptr;            // [0] run-aways this step, [1] n_local inter, [2] n_ghost inter, [3] overflow, [4] invariant violations
-    int *h_counters = nullptr;            // pinned mirror
+    int *h_counters = nullptr;            // pinned, mapped mirror (hd_*: the device's view; k_activity stores into it)
+    int *hd_counters = nullptr;
+    unsigned long long *hd_stepinfo = nullptr;
     int n_inter_local = 0, n_inter_ghost = 0;
     int *d_site_head = nullptr;           // n_ext ints, -1 = empty bucket
     int *d_runaway = nullptr;             // device indices of this step's run-away sites

@@ -94,7 +94,7 @@ __device__ __forceinline__ double hder(const HSlope &g, const double2 r0, const 
 #endif
 __device__ __forceinline__ void rows_s(const uint32_t base, const int m_, double2 &a, double2 &b) {
 #if EAM_EXP_NOCONFLICT
-    const int m = (m_ & ~7) | (int)(threadIdx.x & 7u);
+    const int m = ((m_ - 7) & ~7) | (int)(threadIdx.x & 7u);   // <= m_, at most 14 rows below it: inside the dynamic shared memory
 #else
     const int m = m_;
 #endif

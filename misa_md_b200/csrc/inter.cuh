@@ -42,9 +42,21 @@ static InterHost *IH(misa_b200_ctx *c) { return g_inter_host[c]; }
 // ---- device kernels ---------------------------------------------------------------------------------
 // stepinfo[0] = this sub-box's off-lattice activity (run-aways of this step + listed inter atoms); the caller
 // reduces it (MAX) over the sub-boxes together with stepinfo[1], the dmax2 bit pattern written by k_verlet1
-__global__ void k_activity(int *counters, const int n_listed, unsigned long long *stepinfo) {
+// The step's counters go to the host through MAPPED pinned memory from inside this one-thread kernel (no copy-engine memcpys on
+// the step's stream). Single sub-box: the local words ARE the global ones (stepinfo_g, h_stepinfo); otherwise the all-reduce
+// that follows produces stepinfo_g and k_publish_stepinfo hands it to the host.
+__global__ void k_activity(int *counters, const int n_listed, unsigned long long *stepinfo, unsigned long long *stepinfo_g, int *h_counters,
+                           unsigned long long *h_stepinfo) {
     counters[8] = counters[0] + n_listed;
     stepinfo[0] = (unsigned long long)(counters[0] + n_listed);
+    for (int k = 0; k < 10; k++) h_counters[k] = counters[k];
+    if (stepinfo_g) {
+        stepinfo_g[0] = stepinfo[0]; stepinfo_g[1] = stepinfo[1];
+        h_stepinfo[0] = stepinfo[0]; h_stepinfo[1] = stepinfo[1];
+    }
+}
+__global__ void k_publish_stepinfo(const unsigned long long *stepinfo_g, unsigned long long *h_stepinfo) {
+    h_stepinfo[0] = stepinfo_g[0]; h_stepinfo[1] = stepinfo_g[1];
 }
 __global__ void k_gather_sites(const int n, const int *__restrict__ sites, const Soa s, HostAtom *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -211,6 +211,28 @@ __device__ __forceinline__ unsigned char disp_level_fast(const double dist2, con
     const float l = ceilf(__fmaf_ru(r * 1.00000095f, inv100_a, slack));
     return (unsigned char)(l > 255.0f ? 255 : (int)l);
 }
+// run-away append (atom::decide's displacement test fired) and hot-cell marking, a few dozen atoms of millions per step.
+// Scalars by value on purpose: a reference to a kernel-parameter struct would copy it to local memory in EVERY thread.
+__device__ __noinline__ void verlet1_rare(const int d, const long long cell, const int gx, const int gy, const int gz, const int sy, const int sxc,
+                                          const bool runaway, const bool mark, unsigned char *__restrict__ hot, const unsigned char epoch,
+                                          unsigned long long *__restrict__ mark_count, int *__restrict__ counters, int *__restrict__ runaway_sites,
+                                          const int runaway_cap) {
+    if (runaway) {
+        const int slot = atomicAdd(&counters[0], 1);
+        if (slot < runaway_cap) runaway_sites[slot] = d;
+        else atomicExch(&counters[3], 1);
+    }
+    // (a plain look first: once the cap is passed -- thermalisation transients, when most atoms lie above T -- nobody queues on
+    // the counter any more; it then stands above MARK_CAP, which is what tells the stencil kernels to ignore the map)
+    if (mark && *(volatile unsigned long long *)mark_count <= MARK_CAP && atomicAdd(mark_count, 1ULL) < MARK_CAP) {
+        // a far-displaced atom (a few dozen of 2 M at 300 K): every cell within the stencil reach learns that the cheap
+        // partner bound mark_T does not hold around it. The mark is the step's epoch byte, so the map is never cleared: a
+        // stale byte that aliases 255 steps later only makes a warp keep the global bound (the safe side).
+        for (int dz = -gz; dz <= gz; dz++)
+            for (int dy = -gy; dy <= gy; dy++)
+                for (int dx = -gx; dx <= gx; dx++) hot[cell + ((long long)dz * sy + dy) * sxc + dx] = epoch;
+    }
+}
 // squared displacement of the atom from its ideal site after the drift (0 for vacant sites).
 // KICK2: the second half-kick of the step that just finished (NewtonMotion::secondstep, same f) is applied first --
 // inside a multi-step call the two streaming passes over v and f become one (bit-identical: the same two rounded adds)
@@ -246,30 +268,19 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
     double dist = __dmul_rn(ex, ex);
     dist = __dadd_rn(dist, __dmul_rn(ey, ey));
     dist = __dadd_rn(dist, __dmul_rn(ez, ez));
-    if (dist > g.runaway2) {
-        const int slot = atomicAdd(&counters[0], 1);
-        if (slot < runaway_cap) runaway_sites[slot] = d;
-        else atomicExch(&counters[3], 1);
-    }
     const int lev = disp_level_fast(dist, vp.inv100_a, vp.lev_slack);
     s.ulev[d] = (unsigned char)lev;
-    // (a plain look first: once the cap is passed -- thermalisation transients, when most atoms lie above T -- nobody queues on
-    // the counter any more; it then stands above MARK_CAP, which is what tells the stencil kernels to ignore the map)
-    if (vp.hot && lev > vp.mark_T && *(volatile unsigned long long *)vp.mark_count <= MARK_CAP && atomicAdd(vp.mark_count, 1ULL) < MARK_CAP) {
-        // a far-displaced atom (a few dozen of 2 M at 300 K): every cell within the stencil reach learns that the cheap
-        // partner bound mark_T does not hold around it. The mark is the step's epoch byte, so the map is never cleared: a
-        // stale byte that aliases 255 steps later only makes a warp keep the global bound (the safe side).
-        const long long cell = ((long long)(z + g.gz) * g.sy + (y + g.gy)) * g.sxc + (cx + g.gx);
-        for (int dz = -g.gz; dz <= g.gz; dz++)
-            for (int dy = -g.gy; dy <= g.gy; dy++)
-                for (int dx = -g.gx; dx <= g.gx; dx++) vp.hot[cell + ((long long)dz * g.sy + dy) * g.sxc + dx] = vp.epoch;
-    }
+    // rare paths out of line (they cost the streaming path 14 registers and a quarter of its occupancy when inlined)
+    const bool runaway = dist > g.runaway2, mark = vp.hot && lev > vp.mark_T;
+    if (runaway || mark)
+        verlet1_rare(d, ((long long)(z + g.gz) * g.sy + (y + g.gy)) * g.sxc + (cx + g.gx), g.gx, g.gy, g.gz, g.sy, g.sxc, runaway, mark, vp.hot, vp.epoch,
+                     vp.mark_count, counters, runaway_sites, runaway_cap);
     return dist;
 }
 
 
 template <bool KICK2>
-__global__ void __launch_bounds__(MISA_BLOCK)
+__global__ void __launch_bounds__(MISA_BLOCK, 8)   // 32 registers: eight resident blocks, the latency of the nine loads needs every warp it can get
 k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
           int *__restrict__ runaway_sites, const int runaway_cap, unsigned long long *__restrict__ stepinfo) {
     const int p = blockIdx.x >= blocks_per_parity;
@@ -277,7 +288,19 @@ k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
     const long long c = (long long)b * blockDim.x + threadIdx.x;
     double dist = 0.0;
     if (c < g.n_cells_owned) dist = verlet1_site<KICK2>(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
-    report_max(dist, &stepinfo[1]);
+    // maximum over the BLOCK first: one look at the running maximum per block, not per warp -- 62 500 volatile reads of one word
+    // per launch queue up at a single L2 slice (about one per clock: tens of microseconds of a 60-microsecond kernel)
+    __shared__ double wmax[MISA_BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) dist = fmax(dist, __shfl_xor_sync(0xffffffffu, dist, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = dist;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = wmax[0];
+#pragma unroll
+        for (int w = 1; w < MISA_BLOCK / 32; w++) m = fmax(m, wmax[w]);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+        if (bits > *reinterpret_cast<volatile unsigned long long *>(&stepinfo[1])) atomicMax(&stepinfo[1], bits);
+    }
 }
 // ---- K5 verlet-2: NewtonMotion::secondstep (reference src/newton_motion.cpp:57-74) -------------------
 __global__ void __launch_bounds__(MISA_BLOCK)

@@ -297,16 +297,21 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
             if (cudaCreateTextureObject(objs[k], &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); *objs[k] = 0; }
         }
     }
-    TRY(dmalloc(&c->d_counters, 16));
-    CU(cudaMemset(c->d_counters, 0, 16 * sizeof(int)));
-    CU(cudaMallocHost((void **)&c->h_counters, 16 * sizeof(int)));
-    TRY(dmalloc(&c->d_stepinfo, 4));
-    CU(cudaMemset(c->d_stepinfo, 0, 4 * sizeof(unsigned long long)));
+    // the step's words and the counters share one allocation: [0] activity, [1] dmax2 bits, [2] marking atoms, then the 16
+    // int counters -- so that ONE 28-byte memset in front of k_verlet1 zeroes everything a step accumulates
+    TRY(dmalloc(&c->d_stepinfo, 3 + 8));
+    CU(cudaMemset(c->d_stepinfo, 0, (3 + 8) * sizeof(unsigned long long)));
+    c->d_counters = reinterpret_cast<int *>(c->d_stepinfo + 3);
+    CU(cudaHostAlloc((void **)&c->h_counters, 16 * sizeof(int), cudaHostAllocMapped));
+    memset(c->h_counters, 0, 16 * sizeof(int));
+    CU(cudaHostGetDevicePointer((void **)&c->hd_counters, c->h_counters, 0));
     TRY(dmalloc(&c->d_stepinfo_g, 4));
     CU(cudaMemset(c->d_stepinfo_g, 0, 4 * sizeof(unsigned long long)));
     CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&c->ev_v1, &c->ev_act, &c->ev_hx, &c->ev_rho, &c->ev_hdf}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    CU(cudaMallocHost((void **)&c->h_stepinfo, 4 * sizeof(unsigned long long)));
+    CU(cudaHostAlloc((void **)&c->h_stepinfo, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(c->h_stepinfo, 0, 4 * sizeof(unsigned long long));
+    CU(cudaHostGetDevicePointer((void **)&c->hd_stepinfo, c->h_stepinfo, 0));
     TRY(dmalloc(&c->d_reduce, 8));
     CU(cudaMallocHost((void **)&c->h_reduce, 8 * sizeof(double)));
 
@@ -390,7 +395,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
-    cudaFree(c->d_counters); cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
+    cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
     cudaFree(c->d_minor); cudaFree(c->d_minor_count); cudaFree(c->d_mcount); cudaFree(c->d_mentry);
     cudaFree(c->d_lo_tab); cudaFree(c->d_pair);
     cudaFree(c->d_push_dst); cudaFree(c->d_push_src); cudaFree(c->d_push_code); cudaFree(c->d_flags);
@@ -1604,14 +1609,16 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
 // Enqueued on `st`; the results are in h_counters / h_stepinfo once `st` (or ev_act) has been waited for, and in
 // d_stepinfo_g on the device (kernels of the same step read the global dmax from there).
 static int activity_enqueue(misa_b200_ctx *c, cudaStream_t st) {
-    k_activity<<<1, 1, 0, st>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost, c->d_stepinfo);
+    const bool reduce = c->comm_size > 1 && c->nccl_comm;
+    k_activity<<<1, 1, 0, st>>>(c->d_counters, c->n_inter_local + c->n_inter_ghost, c->d_stepinfo, reduce ? nullptr : c->d_stepinfo_g, c->hd_counters,
+                                c->hd_stepinfo);
     c->launches++;
-    if (c->comm_size > 1 && c->nccl_comm) // [0] activity, [1] dmax2 bit pattern: MAX over the sub-boxes
+    if (reduce) { // [0] activity, [1] dmax2 bit pattern: MAX over the sub-boxes
         NC(g_nccl.AllReduce(c->d_stepinfo, c->d_stepinfo_g, 2, kNcclUint64, kNcclMax, c->nccl_comm, st));
-    else
-        CU(cudaMemcpyAsync(c->d_stepinfo_g, c->d_stepinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(c->h_counters, c->d_counters, 10 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_stepinfo, c->d_stepinfo_g, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        k_publish_stepinfo<<<1, 1, 0, st>>>(c->d_stepinfo_g, c->hd_stepinfo);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
     return 0;
 }
 static int update_activity(misa_b200_ctx *c) {
@@ -1635,8 +1642,7 @@ static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false) {
         vp.mark_T = c->mark_T_used; vp.hot = c->d_hot; vp.epoch = (unsigned char)c->mark_epoch; vp.mark_count = c->d_stepinfo + 2;
         c->mark_valid = true;
     }
-    CU(cudaMemsetAsync(c->d_counters, 0, sizeof(int), c->stream));
-    CU(cudaMemsetAsync(c->d_stepinfo, 0, 3 * sizeof(unsigned long long), c->stream));   // [2]: atoms that marked (kernels.cuh MARK_CAP)
+    CU(cudaMemsetAsync(c->d_stepinfo, 0, 3 * sizeof(unsigned long long) + sizeof(int), c->stream));   // [0..2] + counters[0] (run-aways)
     if (kick2) k_verlet1<true><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
     else k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
     c->launches++;

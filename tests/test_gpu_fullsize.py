@@ -37,7 +37,7 @@ def _whole_box(n, ratio, sigma, steps):
     assert np.array_equal(got["type"], ref["type"]) and np.array_equal(got["id"], ref["id"])
     # step 0: identical inputs, so the 1e-10 bar applies per atom, against the atom's own magnitude
     assert cm.per_atom_rel(got["rho"], ref["rho"]) <= 1e-10
-    assert cm.per_atom_rel(got["df"], ref["df"]) <= 1e-10
+    assert cm.per_atom_rel(got["df"], ref["df"], 1e-3) <= 1e-10
     if sigma:
         assert cm.per_atom_rel(got["f"], ref["f"]) <= 1e-10
     else:   # perfect lattice: away from the solute atoms the force is a sum of O(1) terms that cancels to round-off by
