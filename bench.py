@@ -321,6 +321,9 @@ class Env:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         self.grid = GRIDS[n_gpus]
+        if os.environ.get("BENCH_GRID"):   # experiments only (e.g. "1,1,2": which faces cross NVLink); the contract's grids are GRIDS
+            self.grid = tuple(int(v) for v in os.environ["BENCH_GRID"].split(","))
+            assert self.grid[0] * self.grid[1] * self.grid[2] == n_gpus
         g = self.grid
         self.coord = (self.rank // (g[1] * g[2]), (self.rank // g[2]) % g[1], self.rank % g[2])
         self.lib = mb.load()
@@ -591,6 +594,11 @@ def run_b200(args):
              "world_build_ms": main["world_build_ms"], "stencil_offsets": int(ctx.query("n_off")), "stencil_offsets_full": int(ctx.query("n_full")),
              "ghost_exchange": ("periodic fill in place" if n_gpus == 1 else "direct push over NVLink peer memory (csrc/p2p.cuh)" if ctx.query("p2p") else "staged NCCL send/recv"),
              "max_displacement_A": ctx.query("dmax"), "temperature_K": th["mvv"] * 1.0364269e-4 / ((3 * th["n_atoms"] - 3) * 8.617343e-5)}
+    if os.environ.get("BENCH_P2P_DEBUG") and n_gpus > 1:   # experiments: phase timing of the push kernels (globaltimer stamps)
+        ctx.set_option("p2p_debug", 1)
+        ctx.step(50)
+        state["p2p_push_ns"] = {w + "_" + ph: ctx.query("p2p_dbg_%s_%s" % (w, ph)) for w in ("x", "df") for ph in ("head", "body", "tail", "all")}
+        ctx.set_option("p2p_debug", 0)
     ctx.host_unregister(host)
     ctx.close()
     del host

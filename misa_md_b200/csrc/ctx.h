@@ -72,6 +72,8 @@ struct P2pPeers {
     long long stride;              // field stride of the block (doubles)
     unsigned int mask;             // direction codes in use
     long long spin_limit;          // SM clocks a flag wait may take before it gives up with an error
+    int fence_mode;                // p2p.cuh:p2p_push_tail
+    unsigned long long *dbg;       // phase timing of the push kernels (option "p2p_debug"), else null
 };
 
 struct misa_b200_ctx {
@@ -152,6 +154,9 @@ struct misa_b200_ctx {
     double *d_sendbuf[2] = {nullptr, nullptr}, *d_recvbuf[2] = {nullptr, nullptr};
     size_t halo_buf_elems = 0;
     // direct push of the composed ghost <- owned map into the neighbours' HBM (p2p.cuh)
+    int opt_p2p_debug = 0;
+    int opt_p2p_fence = 2;                // 0: system-scope fence in every CTA of a push kernel; 1: device-scope, the last CTA releases at system scope; 2: ARRIVE from a follow-up kernel
+    int opt_dmax_flags = 1;               // sync-free step over peer memory: displacement maxima travel on the push flags (no all-reduce in front of rho)
     int opt_late = 1;                     // wait for the neighbours' push inside the stencil kernels (interior units first)
     int opt_p2p = -1;                     // -1 / 1: whenever every surrounding sub-box is peer-mapped on this node; 0: NCCL send/recv
     bool p2p_active = false;
@@ -165,6 +170,7 @@ struct misa_b200_ctx {
     P2pPeers p2p{};
     unsigned long long *d_flags = nullptr, p2p_epoch = 0, p2p_ready_sent = 0;   // flags: [0,27) ready, [32,59) arrive, [63] CTA counter
     unsigned int *h_p2p_err = nullptr, *d_p2p_err = nullptr;
+    unsigned long long *d_p2p_dbg = nullptr;   // [2][8]: position / df push
     std::vector<void *> p2p_opened;
     // integrator
     double dt = 0.001;
@@ -189,6 +195,8 @@ struct misa_b200_ctx {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_v1 = nullptr, ev_act = nullptr, ev_hx = nullptr, ev_rho = nullptr, ev_hdf = nullptr;
     unsigned long long *d_stepinfo_g = nullptr; // [0] activity, [1] dmax2 bits: MAX over all sub-boxes (all-reduce result)
+    unsigned long long *d_stepinfo_n = nullptr; // [1] dmax2 bits: MAX over this sub-box and the 26 around it (folded from the push flags)
+    bool dmax_by_flags = false;                 // this step's pushes carry the displacement maxima (sync-free step over peer memory)
     int opt_pipe = 1;
     int opt_overlap = -1;                       // multi-GPU: interior/boundary split with the exchange on stream2 (-1 auto)
     int opt_reserve = 8;                        // SMs the interior stencil launches leave to the exchange kernels

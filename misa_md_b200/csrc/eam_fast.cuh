@@ -277,7 +277,7 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
-    const int lg = base_level(ls);
+    int lg = base_level(ls);                          // with lw.fold_dmax: the own maximum (interior units), widened at the late wait
     const bool hot_ok = hot_map_usable(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
@@ -300,7 +300,11 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         int par;
         long long up;
         unit_split(rl, u, par, up);
-        if (!waited && u >= 2 * rl.split) { late_wait(lw, lane); waited = true; }
+        if (!waited && u >= 2 * rl.split) {
+            const unsigned long long b = late_wait(lw, lane, lw.fold_dmax ? *ls.dmax2_bits : 0ULL);
+            if (lw.fold_dmax) lg = level_of_bits(ls, b);
+            waited = true;
+        }
         const int d0 = region_unit_to_dev(g, rl, up, par, lane);
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
@@ -395,7 +399,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     constexpr bool NEEDTYPE = !SINGLE || !NOVAC;
     const int *offs = offs_h;                         // the distance-sorted full list; every warp loops a prefix of it
     const int n_list = n_off_h, n_near = n_near_h;
-    const int lg = base_level(ls);
+    int lg = base_level(ls);                          // with lw.fold_dmax: the own maximum (interior units), widened at the late wait
     const bool hot_ok = hot_map_usable(ls);
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
@@ -419,7 +423,11 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         int par;
         long long up;
         unit_split(rl, u, par, up);
-        if (!waited && u >= 2 * rl.split) { late_wait(lw, lane); waited = true; }
+        if (!waited && u >= 2 * rl.split) {
+            const unsigned long long b = late_wait(lw, lane, lw.fold_dmax ? *ls.dmax2_bits : 0ULL);
+            if (lw.fold_dmax) lg = level_of_bits(ls, b);
+            waited = true;
+        }
         const int d0 = region_unit_to_dev(g, rl, up, par, lane);
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);

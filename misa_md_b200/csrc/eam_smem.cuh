@@ -175,8 +175,12 @@ __host__ __device__ __forceinline__ void unit_split(const RegionList &rl, const 
 // Ghost push of p2p.cuh consumed INSIDE the stencil kernel: interior units read no ghost site (nor any 32-byte sector that
 // holds one), so they run while the neighbours' stores are still in flight; the first boundary unit of a warp spins on the
 // arrive flags (ld.acquire.sys). The L1 / texture cache is cold for every sector with a ghost in it until then.
-struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; long long limit; };
-__device__ __forceinline__ void late_wait(const LateWait &lw, const int lane) {
+// fold_dmax: the neighbours' displacement maxima arrive with the push (p2p.cuh, P2P_DMAX words, written in front of ARRIVE);
+// late_wait then returns max(own, neighbours') as the partner bound of the boundary units. Interior units need only the own
+// maximum: every partner of theirs is an owned atom.
+struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; long long limit; int fold_dmax; };
+__device__ __forceinline__ unsigned long long late_wait(const LateWait &lw, const int lane, const unsigned long long own_bits = 0) {
+    unsigned long long best = own_bits;
     if (lane < 27 && ((lw.mask >> lane) & 1u)) {
         const unsigned long long *w = lw.flags + 32 + lane;   // P2P_ARRIVE + code
         const long long t0 = clock64();
@@ -185,8 +189,12 @@ __device__ __forceinline__ void late_wait(const LateWait &lw, const int lane) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
             if (v < lw.epoch && clock64() - t0 > lw.limit) { *(volatile unsigned int *)lw.err = 200u + lane; break; }
         } while (v < lw.epoch);
+        if (lw.fold_dmax) { const unsigned long long n = *(volatile const unsigned long long *)(lw.flags + 64 + lane); best = n > best ? n : best; }   // P2P_DMAX + code
     }
     __syncwarp();
+    if (lw.fold_dmax)
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, best, o); best = w > best ? w : best; }
+    return best;
 }
 
 __device__ __forceinline__ int region_unit_to_dev(const Geo &g, const RegionList &rl, const long long u, const int p, const int lane) {
@@ -233,10 +241,13 @@ __device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs
     else { offs = ls.full; n_off = ls.n_full; n_near = ls.near_full; }
 }
 // global displacement level (the bound on the partner atom of any pair)
+__device__ __forceinline__ int level_of_bits(const LevelSel &ls, const unsigned long long bits) {
+    const double d = sqrt(__longlong_as_double((long long)bits)) + 1e-6;
+    return (int)min(ceil(d / ls.step), 1000.0);
+}
 __device__ __forceinline__ int base_level(const LevelSel &ls) {
     if (!ls.dmax2_bits) return ls.host_level;
-    const double d = sqrt(__longlong_as_double((long long)*ls.dmax2_bits)) + 1e-6;
-    return (int)min(ceil(d / ls.step), 1000.0);
+    return level_of_bits(ls, *ls.dmax2_bits);
 }
 // offsets a warp loops: lw = largest displacement level among its own atoms (warp-uniform)
 __device__ __forceinline__ bool hot_map_usable(const LevelSel &ls) { return ls.hot && *ls.hot_count <= MARK_CAP; }

@@ -307,6 +307,8 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     CU(cudaHostGetDevicePointer((void **)&c->hd_counters, c->h_counters, 0));
     TRY(dmalloc(&c->d_stepinfo_g, 4));
     CU(cudaMemset(c->d_stepinfo_g, 0, 4 * sizeof(unsigned long long)));
+    TRY(dmalloc(&c->d_stepinfo_n, 4));
+    CU(cudaMemset(c->d_stepinfo_n, 0, 4 * sizeof(unsigned long long)));
     CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&c->ev_v1, &c->ev_act, &c->ev_hx, &c->ev_rho, &c->ev_hdf}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CU(cudaHostAlloc((void **)&c->h_stepinfo, 4 * sizeof(unsigned long long), cudaHostAllocMapped));
@@ -387,7 +389,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
     cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id); cudaFree(c->s.ulev); cudaFree(c->d_hot); cudaFree(c->d_hot_init);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
-    cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g);
+    cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g); cudaFree(c->d_stepinfo_n);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
     cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
@@ -894,6 +896,16 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "p2p")) c->opt_p2p = value;
     else if (!strcmp(name, "mark")) c->opt_mark = value;
     else if (!strcmp(name, "late")) c->opt_late = value;
+    else if (!strcmp(name, "dmax_flags")) c->opt_dmax_flags = value;
+    else if (!strcmp(name, "p2p_fence")) c->opt_p2p_fence = value;
+    else if (!strcmp(name, "p2p_debug")) {
+        if (value && !c->d_p2p_dbg) {
+            TRY(dmalloc(&c->d_p2p_dbg, 16));
+            const unsigned long long init[16] = {~0ULL, 0, 0, 0, 0, 0, 0, 0, ~0ULL, 0, 0, 0, 0, 0, 0, 0};
+            CU(cudaMemcpy(c->d_p2p_dbg, init, sizeof init, cudaMemcpyHostToDevice));
+        }
+        c->opt_p2p_debug = value;
+    }
     else if (!strcmp(name, "p2p_timeout_s")) { c->opt_p2p_timeout_s = std::max(1, value); c->p2p.spin_limit = (long long)c->opt_p2p_timeout_s * 2000000000LL; }
     else if (!strcmp(name, "minor_staged")) c->opt_minor_staged = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
@@ -933,6 +945,18 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
         *value = (double)n;
     }
     else if (!strcmp(name, "mark_level")) *value = c->mark_valid ? c->mark_T_used : -1;
+    else if (!strncmp(name, "p2p_dbg_", 8)) {   // p2p_dbg_<x|df>_<head|body|tail|all>: mean ns per push since the option was set
+        *value = -1.0;
+        if (c->d_p2p_dbg) {
+            unsigned long long h[16];
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaMemcpy(h, c->d_p2p_dbg, sizeof h, cudaMemcpyDeviceToHost));
+            const int w = !strncmp(name + 8, "df_", 3) ? 8 : 0;
+            const char *ph = name + 8 + (w ? 3 : 2);
+            const int k = !strcmp(ph, "head") ? 3 : !strcmp(ph, "body") ? 4 : !strcmp(ph, "tail") ? 5 : 6;
+            *value = h[w + 7] ? (double)h[w + k] / (double)h[w + 7] : 0.0;
+        }
+    }
     else if (!strcmp(name, "p2p_error")) *value = c->h_p2p_err && *c->h_p2p_err ? (double)*c->h_p2p_err : (double)c->p2p_last_error;
     else if (!strcmp(name, "sym")) *value = planned && sym_active(c, sp) ? 1 : 0;
     else return fail(MISA_B200_EINVAL, std::string("unknown query ") + name);
@@ -1291,9 +1315,17 @@ static bool late_wait_ok(const misa_b200_ctx *c, const StagePlan &sp, bool plann
     if (!(sp.single >= 0 || dilute_ok(c, sp, accum)) || sym_ok(c, sp, accum, so)) return false;
     return make_regions(c->geo, 3).split > 0;
 }
+// Which displacement word a stencil launch of the sync-free step reads. With the maxima travelling on the push flags
+// (dmax_by_flags) a launch that waits inside the kernel starts from the OWN word and widens it at the late wait; a launch
+// behind k_p2p_wait_arrive reads the word that kernel folded.
+static const unsigned long long *stencil_dmax(const misa_b200_ctx *c, const StencilOpt &so, bool late) {
+    if (c->dmax_by_flags && so.late) return late ? c->d_stepinfo + 1 : c->d_stepinfo_n + 1;
+    return so.dmax2;
+}
 static LateWait make_latewait(const misa_b200_ctx *c) {
     LateWait lw;
     lw.flags = c->d_flags; lw.epoch = c->p2p_epoch; lw.mask = c->p2p.mask; lw.err = c->d_p2p_err; lw.limit = c->p2p.spin_limit;
+    lw.fold_dmax = c->dmax_by_flags ? 1 : 0;
     return lw;
 }
 
@@ -1351,7 +1383,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const bool novac = no_vacancy(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
         const RegionList rl = make_regions(g, late ? 3 : so.region);
-        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
         if (sym_ok(c, sp, accum, so)) {
             TRY(sym_scratch(c));
@@ -1403,7 +1435,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
         const bool novac = no_vacancy(c);
         const RegionList rl = make_regions(g, so.region);
-        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
 #define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
 #define RHO_X(T, N) k_rho_s<true, true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
@@ -1480,7 +1512,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
         const RegionList rl = make_regions(g, 0), ra = make_regions_sym(c);
-        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         const bool dil = sp.single < 0, novac = no_vacancy(c);
         const MinorList ml = dil ? minor_list(c) : MinorList();
         const SymPlan sy = {c->d_pair, c->d_lo_tab, c->n_half, g.n_ext};
@@ -1509,7 +1541,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
 #endif
         const RegionList rl = make_regions(g, late ? 3 : so.region);
-        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         const MinorList ml = minor_list(c);
         if (rl.units > 0) {
             if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml, lw);
@@ -1519,7 +1551,12 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         }
         // atoms of a minority species: ALL of them with the launch that runs after the df halo has arrived (the whole-box
         // launch or the boundary one), one warp per atom
-        if (so.region != 1) TRY(launch_force_minor(c, sp, offs, n_off, ls, tex));
+        if (so.region != 1) {
+            if (c->dmax_by_flags && so.late && late) {   // k_force_minor has no late wait: fold the neighbours' maxima in front of it
+                TRY(p2p_wait(c, c->stream));
+                TRY(launch_force_minor(c, sp, offs, n_off, make_levelsel(c, c->d_stepinfo_n + 1), tex));
+            } else TRY(launch_force_minor(c, sp, offs, n_off, ls, tex));
+        }
         return 0;
     }
     // non-dilute alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the
@@ -1534,7 +1571,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
 #endif
         const RegionList rl = make_regions(g, late ? 3 : so.region);
-        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
 #define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); \
                            else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw); } while (0)
@@ -1552,7 +1589,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
         const bool novac = no_vacancy(c);
         const RegionList rl = make_regions(g, so.region);
-        const LevelSel ls = make_levelsel(c, so.dmax2);
+        const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
 #define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
 #define FORCE_X(T, N) k_force_s<true, false, T, N><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
@@ -1744,7 +1781,8 @@ extern "C" int misa_b200_prepare(misa_b200_ctx *c) {
 static bool pipe_ok(const misa_b200_ctx *c) {
     StagePlan sp;
     size_t sb;
-    return c->opt_pipe && c->opt_fast && c->opt_prune && c->opt_fuse && c->tex_all && !c->prof_on && !has_inter(c) && !c->inter_active &&
+    // (profiling keeps the sync-free step: the slot events are recorded on the main stream between its kernels)
+    return c->opt_pipe && c->opt_fast && c->opt_prune && c->opt_fuse && c->tex_all && !has_inter(c) && !c->inter_active &&
            c->stream2 && make_plan(c, sp, sb);
 }
 // kick2_in: the previous step of this call left its second half-kick to this step's k_verlet1<true>;
@@ -1769,24 +1807,29 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
     boundary.region = 2; boundary.dmax2 = c->d_stepinfo_g + 1;
     if (!overlap) {
         if (p2p && c->stream2) {
-            // the all-reduce of the activity / displacement words (NCCL, latency-bound) runs beside the position push, which
-            // does not touch the communicator; rho needs both (it reads the global maximum)
+            // The all-reduce of the activity / displacement words (NCCL, latency-bound) runs on stream2 and only the HOST waits
+            // for it, at the end of the step (has anything run away anywhere?). The stencil kernels no longer do: the partner
+            // bound of their pruning is the maximum over this sub-box and the 26 around it -- every partner of an owned atom
+            // lives there -- and those maxima travel with the position push (P2P_DMAX words in front of ARRIVE). Option
+            // "dmax_flags" 0 restores the all-reduce in front of rho.
             CU(cudaEventRecord(c->ev_v1, c->stream));
             CU(cudaStreamWaitEvent(c->stream2, c->ev_v1, 0));
             TRY(activity_enqueue(c, c->stream2));
             CU(cudaEventRecord(c->ev_act, c->stream2));
-            TRY(p2p_push(c, true, c->stream));
-            CU(cudaStreamWaitEvent(c->stream, c->ev_act, 0));
+            c->dmax_by_flags = c->opt_dmax_flags != 0;
+            { Slot sl(c, MISA_B200_K_HALO_X); TRY(p2p_push(c, true, c->stream)); }
+            if (!c->dmax_by_flags) CU(cudaStreamWaitEvent(c->stream, c->ev_act, 0));
             whole.late = true;                      // the wait for the neighbours' pushes moves into the stencil kernels
             TRY(launch_rho(c, true, false, whole));
-            TRY(p2p_push(c, false, c->stream));
+            { Slot sl(c, MISA_B200_K_HALO_DF); TRY(p2p_push(c, false, c->stream)); }
             TRY(launch_force(c, false, whole));
+            c->dmax_by_flags = false;
         } else {
             TRY(activity_enqueue(c, c->stream));
             CU(cudaEventRecord(c->ev_act, c->stream));
-            TRY(halo_forward(c, true));
+            { Slot sl(c, MISA_B200_K_HALO_X); TRY(halo_forward(c, true)); }
             TRY(launch_rho(c, true, false, whole));
-            TRY(halo_forward(c, false));
+            { Slot sl(c, MISA_B200_K_HALO_DF); TRY(halo_forward(c, false)); }
             TRY(launch_force(c, false, whole));
         }
         // ghost x and df are free for the next step's two exchanges -- only when that step follows inside this call:

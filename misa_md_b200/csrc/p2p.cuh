@@ -22,7 +22,8 @@
 
 #define P2P_READY 0
 #define P2P_ARRIVE 32
-#define P2P_FLAG_WORDS 64
+#define P2P_DMAX 64          // [64, 91): the origin's largest squared displacement of the step (bit pattern), written before ARRIVE
+#define P2P_FLAG_WORDS 128
 // A peer that never answers ends the wait with an error, not a hang: P2pPeers::spin_limit SM clocks (default 30 s; option
 // "p2p_timeout_s" / MISA_B200_OPTS). A push kernel whose wait for READY timed out stores NOTHING into the neighbours'
 // ghosts and does not signal ARRIVE -- the neighbour may still be reading them -- so rank skew beyond the limit is an
@@ -54,63 +55,117 @@ __global__ void k_p2p_ready(const P2pPeers pp, const unsigned long long epoch) {
     __threadfence_system();
     st_release_sys(pp.flags[26 - k] + P2P_READY + k, epoch);
 }
-// wait until every origin's stores into my ghosts are performed
-__global__ void k_p2p_wait_arrive(const P2pPeers pp, const unsigned long long epoch, const unsigned long long *__restrict__ my_flags,
-                                  unsigned int *__restrict__ err) {
+// fence_mode 2: the ARRIVE flags as a kernel of their own, stream-ordered behind the push (its stores are complete at the
+// kernel boundary)
+__global__ void k_p2p_arrive(const P2pPeers pp, const unsigned long long epoch, const unsigned int *__restrict__ err, const unsigned long long *__restrict__ dmax2) {
     const int k = threadIdx.x;
-    if (k >= 27 || !((pp.mask >> k) & 1u)) return;
-    p2p_wait(my_flags + P2P_ARRIVE + k, epoch, err, 100u + k, pp.spin_limit);
+    if (*(volatile const unsigned int *)err != 0) return;
+    __threadfence_system();
+    if (k < 27 && ((pp.mask >> k) & 1u)) {
+        if (dmax2) *(volatile unsigned long long *)(pp.flags[k] + P2P_DMAX + k) = *dmax2;
+        st_release_sys(pp.flags[k] + P2P_ARRIVE + k, epoch);
+    }
+}
+// wait until every origin's stores into my ghosts are performed
+// fold != null: also leave max(own word, the neighbours' P2P_DMAX words) in fold[1] (bit patterns of non-negative doubles
+// order like integers) -- the partner bound for a stencil launch that does not wait inside the kernel
+__global__ void k_p2p_wait_arrive(const P2pPeers pp, const unsigned long long epoch, const unsigned long long *__restrict__ my_flags,
+                                  unsigned int *__restrict__ err, const unsigned long long *__restrict__ own_dmax2, unsigned long long *__restrict__ fold) {
+    const int k = threadIdx.x;
+    unsigned long long v = 0;
+    if (k < 27 && ((pp.mask >> k) & 1u)) {
+        p2p_wait(my_flags + P2P_ARRIVE + k, epoch, err, 100u + k, pp.spin_limit);
+        if (fold) v = *(volatile const unsigned long long *)(my_flags + P2P_DMAX + k);
+    }
+    if (!fold) return;
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    if (k == 0) fold[1] = v > *own_dmax2 ? v : *own_dmax2;
 }
 // head of a push kernel: every destination has freed its ghosts; tail: the LAST CTA to finish tells every destination
+// ---- optional phase timing of the push kernels (option "p2p_debug"; off: dbg == nullptr): %globaltimer stamps, folded over the
+//      CTAs with atomics, accumulated by the last CTA. dbg[0] min start, [1] max "READY seen", [2] max "stores issued",
+//      [3..6] sums of (head wait, body, tail, whole) in ns, [7] launches -------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // returns false (for the whole CTA) when a destination never freed its ghosts: the caller must not store into them
 __device__ __forceinline__ bool p2p_push_head(const P2pPeers &pp, const unsigned long long epoch, const unsigned long long *my_flags, unsigned int *err) {
     __shared__ int timed_out;
     const int k = threadIdx.x;
-    if (k == 0) timed_out = 0;
+    if (k == 0) { timed_out = 0; if (pp.dbg) atomicMin(pp.dbg, gtime()); }
     __syncthreads();
     if (k < 27 && ((pp.mask >> k) & 1u) && !p2p_wait(my_flags + P2P_READY + k, epoch, err, 1u + k, pp.spin_limit)) timed_out = 1;
     __syncthreads();
+    if (k == 0 && pp.dbg) atomicMax(pp.dbg + 1, gtime());
     return timed_out == 0;
 }
-__device__ __forceinline__ void p2p_push_tail(const P2pPeers &pp, const unsigned long long epoch, unsigned int *done, const unsigned int *err) {
+// `dmax2`: when non-null, the word k_verlet1 of this step left (this sub-box's largest squared displacement): the last CTA hands
+// it to every destination in front of the ARRIVE flag, so that a consumer that has acquired ARRIVE also holds its neighbours'
+// maxima -- the partner bound of the stencil pruning without an all-reduce in front of the stencil kernels.
+__device__ __forceinline__ void p2p_push_tail(const P2pPeers &pp, const unsigned long long epoch, unsigned int *done, const unsigned int *err,
+                                              const unsigned long long *dmax2 = nullptr) {
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();                      // this CTA's stores are performed at their destinations (cumulative over the barrier)
+        if (pp.dbg) atomicMax(pp.dbg + 2, gtime());
+        // This CTA's stores happen before its ticket (barrier above, release below), every ticket happens before the last CTA's
+        // flag stores (its acquire), and those are system-scope releases: causality order carries all CTAs' stores to whoever
+        // acquires ARRIVE. fence_mode 0 makes every CTA's fence a system-scope one (the round-1 protocol; measured: the tail of
+        // the kernel then takes 25 us -- 300 concurrent MEMBAR.SYS), 1 keeps them at device scope.
+        if (pp.fence_mode == 0) __threadfence_system(); else __threadfence();
         last = atomicAdd(done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!last) return;
     const int k = threadIdx.x;
     if (k == 0) *done = 0;                           // next exchange (stream-ordered after this kernel)
+    if (pp.fence_mode == 2) return;                  // ARRIVE is posted by k_p2p_arrive, behind the kernel boundary
     __threadfence_system();
     if (*(volatile const unsigned int *)err != 0) return;   // some CTA gave up on READY: its part was not stored, nothing ARRIVEd
-    if (k < 27 && ((pp.mask >> k) & 1u)) st_release_sys(pp.flags[k] + P2P_ARRIVE + k, epoch);
+    if (k < 27 && ((pp.mask >> k) & 1u)) {
+        if (dmax2) *(volatile unsigned long long *)(pp.flags[k] + P2P_DMAX + k) = *dmax2;   // ordered before the release below
+        st_release_sys(pp.flags[k] + P2P_ARRIVE + k, epoch);
+    }
+    if (pp.dbg) {
+        __syncthreads();
+        if (k == 0) {
+            const unsigned long long t3 = gtime(), t0 = pp.dbg[0], t1 = pp.dbg[1], t2 = pp.dbg[2];
+            pp.dbg[3] += t1 - t0; pp.dbg[4] += t2 - t1; pp.dbg[5] += t3 - t2; pp.dbg[6] += t3 - t0; pp.dbg[7] += 1;
+            pp.dbg[0] = ~0ULL; pp.dbg[1] = 0; pp.dbg[2] = 0;
+        }
+    }
 }
 
-__global__ void __launch_bounds__(MISA_BLOCK)
+// Persistent grid (at most two CTAs per SM, grid-stride over the map): every CTA pays one READY check (system-scope acquire
+// loads) in front and one system-scope fence + ticket behind its stores -- with one CTA per 256 sites (1 500 CTAs at 100^3 cells)
+// those fixed costs, not the 12 MB of stores, were the 35-55 us the exchange took on two GPUs (profiles/r02e_*, r02f_*).
+// TYPES: also push the species byte. The sync-free step leaves it out: it only runs while nothing is off-lattice anywhere, so no
+// site changes its occupant between two of its exchanges (a run-away sends every sub-box through the serial path, whose
+// exchange carries the bytes) -- and single-byte stores into a neighbour's HBM are the slowest part of the push.
+#define P2P_PUSH_THREADS 512
+template <bool TYPES>
+__global__ void __launch_bounds__(P2P_PUSH_THREADS)
 k_p2p_push_x(const P2pPeers pp, const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code, const Soa s,
-             const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err) {
+             const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err,
+             const unsigned long long *__restrict__ dmax2) {
     const bool ok = p2p_push_head(pp, epoch, my_flags, err);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ok && i < n) {
-        const int a = src[i], b = dst[i], k = code[i];
-        double x = s.x[0][a], y = s.x[1][a], z = s.x[2][a];
-        if (pp.shift[k][0] != 0.0) x = __dadd_rn(x, pp.shift[k][0]);
-        if (pp.shift[k][1] != 0.0) y = __dadd_rn(y, pp.shift[k][1]);
-        if (pp.shift[k][2] != 0.0) z = __dadd_rn(z, pp.shift[k][2]);
-        double *P = pp.xyzd[k];
-        P[b] = x; P[pp.stride + b] = y; P[2 * pp.stride + b] = z;
-        pp.type[k][b] = s.type[a];
-    }
-    p2p_push_tail(pp, epoch, done, err);
+    if (ok)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int a = src[i], b = dst[i], k = code[i];
+            double x = s.x[0][a], y = s.x[1][a], z = s.x[2][a];
+            if (pp.shift[k][0] != 0.0) x = __dadd_rn(x, pp.shift[k][0]);
+            if (pp.shift[k][1] != 0.0) y = __dadd_rn(y, pp.shift[k][1]);
+            if (pp.shift[k][2] != 0.0) z = __dadd_rn(z, pp.shift[k][2]);
+            double *P = pp.xyzd[k];
+            P[b] = x; P[pp.stride + b] = y; P[2 * pp.stride + b] = z;
+            if (TYPES) pp.type[k][b] = s.type[a];
+        }
+    p2p_push_tail(pp, epoch, done, err, dmax2);
 }
-__global__ void __launch_bounds__(MISA_BLOCK)
+__global__ void __launch_bounds__(P2P_PUSH_THREADS)
 k_p2p_push_df(const P2pPeers pp, const int n, const int *__restrict__ dst, const int *__restrict__ src, const int8_t *__restrict__ code, const Soa s,
               const unsigned long long epoch, unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ done, unsigned int *__restrict__ err) {
     const bool ok = p2p_push_head(pp, epoch, my_flags, err);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ok && i < n) pp.xyzd[code[i]][3 * pp.stride + dst[i]] = s.df[src[i]];
+    if (ok)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pp.xyzd[code[i]][3 * pp.stride + dst[i]] = s.df[src[i]];
     p2p_push_tail(pp, epoch, done, err);
 }
 
@@ -248,16 +303,26 @@ static int p2p_push(misa_b200_ctx *c, bool positions, cudaStream_t st) {
         c->p2p_ready_sent = e;
         c->launches++;
     }
-    const int nb = (c->n_push + MISA_BLOCK - 1) / MISA_BLOCK;
+    const int nb = std::max(1, std::min((c->n_push + P2P_PUSH_THREADS - 1) / P2P_PUSH_THREADS, 2 * std::max(c->sm_count, 1)));
+    c->p2p.fence_mode = c->opt_p2p_fence;
+    c->p2p.dbg = c->opt_p2p_debug && c->d_p2p_dbg ? c->d_p2p_dbg + (positions ? 0 : 8) : nullptr;
     unsigned int *done = reinterpret_cast<unsigned int *>(c->d_flags + P2P_FLAG_WORDS - 1);
-    if (positions) k_p2p_push_x<<<nb, MISA_BLOCK, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
-    else k_p2p_push_df<<<nb, MISA_BLOCK, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
+    // inside the sync-free step the push carries this sub-box's displacement maximum along (dmax_by_flags)
+    if (positions && c->dmax_by_flags)   // the sync-free step: no species bytes (see k_p2p_push_x)
+        k_p2p_push_x<false><<<nb, P2P_PUSH_THREADS, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err, c->d_stepinfo + 1);
+    else if (positions)
+        k_p2p_push_x<true><<<nb, P2P_PUSH_THREADS, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err, nullptr);
+    else k_p2p_push_df<<<nb, P2P_PUSH_THREADS, 0, st>>>(c->p2p, c->n_push, c->d_push_dst, c->d_push_src, c->d_push_code, c->s, e, c->d_flags, done, c->d_p2p_err);
     c->launches++;
+    if (c->p2p.fence_mode == 2) {
+        k_p2p_arrive<<<1, 32, 0, st>>>(c->p2p, e, c->d_p2p_err, positions && c->dmax_by_flags ? c->d_stepinfo + 1 : nullptr);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     return 0;
 }
 static int p2p_wait(misa_b200_ctx *c, cudaStream_t st) {
-    k_p2p_wait_arrive<<<1, 32, 0, st>>>(c->p2p, c->p2p_epoch, c->d_flags, c->d_p2p_err);
+    k_p2p_wait_arrive<<<1, 32, 0, st>>>(c->p2p, c->p2p_epoch, c->d_flags, c->d_p2p_err, c->d_stepinfo + 1, c->dmax_by_flags ? c->d_stepinfo_n : nullptr);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
