@@ -72,6 +72,7 @@ struct P2pPeers {
     long long stride;              // field stride of the block (doubles)
     unsigned int mask;             // direction codes in use
     long long spin_limit;          // SM clocks a flag wait may take before it gives up with an error
+    unsigned int *fault;           // device word: a READY gate timed out -- producers that push from inside store nothing
     int fence_mode;                // p2p.cuh:p2p_push_tail
     unsigned long long *dbg;       // phase timing of the push kernels (option "p2p_debug"), else null
 };
@@ -171,6 +172,9 @@ struct misa_b200_ctx {
     unsigned long long *d_flags = nullptr, p2p_epoch = 0, p2p_ready_sent = 0;   // flags: [0,27) ready, [32,59) arrive, [63] CTA counter
     unsigned int *h_p2p_err = nullptr, *d_p2p_err = nullptr;
     unsigned long long *d_p2p_dbg = nullptr;   // [2][8]: position / df push
+    P2pPeers *d_p2p_dev = nullptr;             // device copy of `p2p` for the producers that push from inside (kernels.cuh:push_site)
+    unsigned int *d_p2p_fault = nullptr;
+    int opt_push_fused = 1;                    // sync-free step: k_verlet1 pushes positions, k_rho_f's epilogue pushes df, the stencil kernels post ARRIVE
     std::vector<void *> p2p_opened;
     // integrator
     double dt = 0.001;

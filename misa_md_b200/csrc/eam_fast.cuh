@@ -296,6 +296,7 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     const double2 *__restrict__ g_herm = sp.g_elec[0];
     const size_t tstride = (size_t)tb.n_r + 1;
     bool waited = lw.flags == nullptr;
+    post_arrive(lw);
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         int par;
         long long up;
@@ -384,7 +385,16 @@ EAM_UNROLL(2)
         }
         if (ACCUM) acc += s.rho[d];
         s.rho[d] = acc;
-        if (FUSE_DF) s.df[d] = d_embed(tb, ti, acc);
+        if (FUSE_DF) {
+            const double dfv = d_embed(tb, ti, acc);
+            s.df[d] = dfv;
+            if (lw.push_df && (rl.split <= 0 || u >= 2 * rl.split)) {   // interior units hold no band site
+                const int rem = d - (par ? (int)g.H : 0), cxe = rem % g.sxc, r2 = rem / g.sxc;
+                const int cx = cxe - g.gx, y = r2 % g.sy - g.gy, z = r2 / g.sy - g.gz;
+                if (cx < g.gx || cx >= g.nx - g.gx || y < g.gy || y >= g.ny - g.gy || z < g.gz || z >= g.nz - g.gz)
+                    push_site<1>(lw.push_df, d, cx, y, z, g.nx, g.ny, g.nz, g.gx, g.gy, g.gz, g.sxc, g.sy, 3, dfv, 0.0, 0.0);
+            }
+        }
     }
 }
 
@@ -419,6 +429,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const double2 *__restrict__ g_herm = sp.g_elec[0];
     const size_t tstride = (size_t)tb.n_r + 1;
     bool waited = lw.flags == nullptr;
+    post_arrive(lw);
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
         int par;
         long long up;

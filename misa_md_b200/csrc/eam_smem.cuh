@@ -178,7 +178,20 @@ __host__ __device__ __forceinline__ void unit_split(const RegionList &rl, const 
 // fold_dmax: the neighbours' displacement maxima arrive with the push (p2p.cuh, P2P_DMAX words, written in front of ARRIVE);
 // late_wait then returns max(own, neighbours') as the partner bound of the boundary units. Interior units need only the own
 // maximum: every partner of theirs is an owned atom.
-struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; long long limit; int fold_dmax; };
+// post / post_epoch / post_dmax: the stencil kernel's first CTA posts the ARRIVE flags of the push its PREDECESSOR in the stream
+// did from inside (k_verlet1's positions, k_rho_f's df): that kernel is complete, its stores are performed. push_df: k_rho_f's
+// epilogue stores the new df of band sites into the neighbours' ghosts (kernels.cuh:push_site).
+struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; long long limit; int fold_dmax;
+                  const P2pPeers *post; unsigned long long post_epoch; const unsigned long long *post_dmax; const P2pPeers *push_df; };
+__device__ __forceinline__ void post_arrive(const LateWait &lw) {
+    if (!lw.post || blockIdx.x != 0 || threadIdx.x >= 27) return;
+    const int k = threadIdx.x;
+    const P2pPeers *pp = lw.post;
+    if (!((pp->mask >> k) & 1u) || *pp->fault) return;
+    __threadfence_system();
+    if (lw.post_dmax) *(volatile unsigned long long *)(pp->flags[k] + 64 + k) = *lw.post_dmax;   // P2P_DMAX + code, in front of the release
+    st_release_sys(pp->flags[k] + 32 + k, lw.post_epoch);                                         // P2P_ARRIVE + code
+}
 __device__ __forceinline__ unsigned long long late_wait(const LateWait &lw, const int lane, const unsigned long long own_bits = 0) {
     unsigned long long best = own_bits;
     if (lane < 27 && ((lw.mask >> lane) & 1u)) {

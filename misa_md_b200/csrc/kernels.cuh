@@ -183,7 +183,8 @@ k_force(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ of
 //      k_decide_vacate after the list has been sorted into the reference's k,j,i order. ------------------
 #define MARK_CAP 4096     // marking atoms per step; beyond it the map is void (stepinfo[2] tells the stencil kernels)
 struct VerletPar { double dt; double c[MISA_MAX_TYPES]; int mark_T; unsigned char *hot; unsigned char epoch; unsigned long long *mark_count;
-                   float inv100_a, lev_slack; };   // 100 / a and 2e-4 / a, both rounded up (disp_level_fast)
+                   float inv100_a, lev_slack;      // 100 / a and 2e-4 / a, both rounded up (disp_level_fast)
+                   const P2pPeers *push; };        // non-null: band sites store their new position into the neighbours' ghosts (push_site)
 // dt / (2 m) of species t WITHOUT indexing the kernel parameter dynamically: `vp.c[t]` made the compiler copy the whole
 // parameter struct to local memory in every thread (9 STL + 1 LDL per atom in the SASS of the round-1 kernels)
 __device__ __forceinline__ double kick_coef(const VerletPar &vp, const int t) { return t == 0 ? vp.c[0] : (t == 1 ? vp.c[1] : vp.c[2]); }
@@ -211,6 +212,26 @@ __device__ __forceinline__ unsigned char disp_level_fast(const double dist2, con
     const float l = ceilf(__fmaf_ru(r * 1.00000095f, inv100_a, slack));
     return (unsigned char)(l > 255.0f ? 255 : (int)l);
 }
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// ---- ghost push from INSIDE the producing kernel (p2p.cuh has the protocol; this is its data movement without a kernel of its
+//      own). An owned site within the ghost width of a face is the origin of a ghost in up to seven of the 26 surrounding
+//      sub-boxes: per dimension it either stays (s = 0) or, from the low band, lands n cells higher in the sub-box below
+//      (origin code s = +1) -- from the high band n cells lower in the one above (s = -1); every combination except (0,0,0) is
+//      one destination. That arithmetic map equals the composition of the reference's three staged exchanges
+//      (misa_b200_plan_push; tests/test_host_logic.py checks the two against each other). Scalars by value: see verlet1_rare.
+//      nf fields (3 for positions, 1 for df) at field stride pp->stride from `field0`; positions carry the image shift. ------
+struct P2pPeers;
+template <int NF>
+__device__ __noinline__ void push_site(const P2pPeers *__restrict__ pp, const int d, const int cx, const int y, const int z, const int nx, const int ny,
+                                       const int nz, const int gx, const int gy, const int gz, const int sxc, const int sy, const int field0,
+                                       const double v0, const double v1, const double v2);
 // run-away append (atom::decide's displacement test fired) and hot-cell marking, a few dozen atoms of millions per step.
 // Scalars by value on purpose: a reference to a kernel-parameter struct would copy it to local memory in EVERY thread.
 __device__ __noinline__ void verlet1_rare(const int d, const long long cell, const int gx, const int gy, const int gz, const int sy, const int sxc,
@@ -236,7 +257,7 @@ __device__ __noinline__ void verlet1_rare(const int d, const long long cell, con
 // squared displacement of the atom from its ideal site after the drift (0 for vacant sites).
 // KICK2: the second half-kick of the step that just finished (NewtonMotion::secondstep, same f) is applied first --
 // inside a multi-step call the two streaming passes over v and f become one (bit-identical: the same two rounded adds)
-template <bool KICK2>
+template <bool KICK2, bool PUSH>
 __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const VerletPar &vp, const int p, const long long c,
                                                int *__restrict__ counters, int *__restrict__ runaway_sites, const int runaway_cap) {
     int cx, y, z;
@@ -259,6 +280,8 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) { s.v[k][d] = v[k]; s.x[k][d] = x[k]; }
+    if (PUSH && (cx < g.gx || cx >= g.nx - g.gx || y < g.gy || y >= g.ny - g.gy || z < g.gz || z >= g.nz - g.gz))
+        push_site<3>(vp.push, d, cx, y, z, g.nx, g.ny, g.nz, g.gx, g.gy, g.gz, g.sxc, g.sy, 0, x[0], x[1], x[2]);
     // ideal site, reference src/atom.cpp:34-38: i is the doubled-x sub-box index
     const long long i = 2LL * cx + p;
     const double xt = __dmul_rn(__dmul_rn((double)(i + 2LL * g.lo[0]), 0.5), g.a);
@@ -279,15 +302,17 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
 }
 
 
-template <bool KICK2>
-__global__ void __launch_bounds__(MISA_BLOCK, 8)   // 32 registers: eight resident blocks, the latency of the nine loads needs every warp it can get
+// PUSH: band sites also store their new position into the neighbours' ghosts (VerletPar::push) -- a variant of its own so that
+// the single-sub-box kernel keeps its 32 registers
+template <bool KICK2, bool PUSH = false>
+__global__ void __launch_bounds__(MISA_BLOCK, PUSH ? 5 : 8)   // 32 registers: eight resident blocks, the latency of the nine loads needs every warp it can get
 k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
           int *__restrict__ runaway_sites, const int runaway_cap, unsigned long long *__restrict__ stepinfo) {
     const int p = blockIdx.x >= blocks_per_parity;
     const int b = blockIdx.x - p * blocks_per_parity;
     const long long c = (long long)b * blockDim.x + threadIdx.x;
     double dist = 0.0;
-    if (c < g.n_cells_owned) dist = verlet1_site<KICK2>(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
+    if (c < g.n_cells_owned) dist = verlet1_site<KICK2, PUSH>(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
     // maximum over the BLOCK first: one look at the running maximum per block, not per warp -- 62 500 volatile reads of one word
     // per launch queue up at a single L2 slice (about one per clock: tens of microseconds of a 60-microsecond kernel)
     __shared__ double wmax[MISA_BLOCK / 32];

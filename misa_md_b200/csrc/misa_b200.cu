@@ -898,6 +898,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "late")) c->opt_late = value;
     else if (!strcmp(name, "dmax_flags")) c->opt_dmax_flags = value;
     else if (!strcmp(name, "p2p_fence")) c->opt_p2p_fence = value;
+    else if (!strcmp(name, "push_fused")) c->opt_push_fused = value;
     else if (!strcmp(name, "p2p_debug")) {
         if (value && !c->d_p2p_dbg) {
             TRY(dmalloc(&c->d_p2p_dbg, 16));
@@ -1298,6 +1299,9 @@ struct StencilOpt {                 // how one stencil launch deviates from "who
     const unsigned long long *dmax2 = nullptr;
     int reserve_sms = 0;            // leave this many SMs free (the persistent CTAs would otherwise starve the exchange kernels on stream2)
     bool late = false;              // the ghost push this launch consumes has been issued but not waited for (p2p.cuh)
+    bool fused = false;             // that push was done from inside the producing kernel: this launch posts its ARRIVE flags (post_epoch,
+    unsigned long long post_epoch = 0;   // post_dmax) and, for rho + df, pushes df from its epilogue
+    const unsigned long long *post_dmax = nullptr;
 };
 // ---- pair-symmetric passes (eam_sym.cuh) --------------------------------------------------------------------------
 // One species (or a dilute alloy, whose main loop is the majority species'), overwrite semantics, the whole sub-box in
@@ -1323,12 +1327,26 @@ static const unsigned long long *stencil_dmax(const misa_b200_ctx *c, const Sten
     return so.dmax2;
 }
 static LateWait make_latewait(const misa_b200_ctx *c) {
-    LateWait lw;
+    LateWait lw = LateWait();
     lw.flags = c->d_flags; lw.epoch = c->p2p_epoch; lw.mask = c->p2p.mask; lw.err = c->d_p2p_err; lw.limit = c->p2p.spin_limit;
     lw.fold_dmax = c->dmax_by_flags ? 1 : 0;
     return lw;
 }
 
+// The push hooks of a stencil launch in the fused sync-free step. Waiting inside the kernel (late): its first CTA posts the
+// ARRIVE flags. Waiting in front of it: a tiny kernel posts them BEFORE the wait kernel (both neighbours wait for each other's
+// flags -- posting from behind the wait would deadlock).
+static int fused_hooks(misa_b200_ctx *c, const StencilOpt &so, bool late, bool push_df, LateWait &lw) {
+    if (!so.fused) return 0;
+    if (late) { lw.post = c->d_p2p_dev; lw.post_epoch = so.post_epoch; lw.post_dmax = so.post_dmax; }
+    else {
+        k_p2p_arrive<<<1, 32, 0, c->stream>>>(c->p2p, so.post_epoch, c->d_p2p_err, so.post_dmax);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (push_df) lw.push_df = c->d_p2p_dev;
+    return 0;
+}
 static int sym_scratch(misa_b200_ctx *c) {
     const size_t need = (size_t)c->n_half * (((size_t)c->geo.n_ext + 31) / 32 * 32);
     if (c->pair_elems >= need) return 0;
@@ -1376,8 +1394,9 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
     size_t sb;
     const bool planned_any = make_plan(c, sp, sb);
     const bool late = late_wait_ok(c, sp, planned_any, accum, so);
+    LateWait lw = late ? make_latewait(c) : LateWait();
+    TRY(fused_hooks(c, so, late, fuse_df, lw));
     if (so.late && !late) TRY(p2p_wait(c, c->stream));   // the push this launch consumes: waited for in front of it
-    const LateWait lw = late ? make_latewait(c) : LateWait();
     if (c->opt_fast && c->tex_all && planned_any) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
@@ -1505,8 +1524,9 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     size_t sb;
     const bool planned_any = make_plan(c, sp, sb);
     const bool late = late_wait_ok(c, sp, planned_any, accum, so);
+    LateWait lw = late ? make_latewait(c) : LateWait();
+    TRY(fused_hooks(c, so, late, false, lw));
     if (so.late && !late) TRY(p2p_wait(c, c->stream));   // the push this launch consumes: waited for in front of it
-    const LateWait lw = late ? make_latewait(c) : LateWait();
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && sym_ok(c, sp, accum, so)) {
         TRY(sym_scratch(c));
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
@@ -1545,7 +1565,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         const MinorList ml = minor_list(c);
         if (rl.units > 0) {
             if (no_vacancy(c)) k_force_f<true, true, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml, lw);
-            else k_force_f<true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml);
+            else k_force_f<true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, ml, lw);
             c->launches++;
             CU(cudaGetLastError());
         }
@@ -1634,7 +1654,7 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
     VerletPar vp;
     vp.dt = c->dt;
     for (int i = 0; i < MISA_MAX_TYPES; i++) vp.c[i] = c->dt_inv_m[i];
-    vp.mark_T = 0; vp.hot = nullptr; vp.epoch = 0; vp.mark_count = nullptr;
+    vp.mark_T = 0; vp.hot = nullptr; vp.epoch = 0; vp.mark_count = nullptr; vp.push = nullptr;
     // level arithmetic of k_verlet1 in single precision, every constant rounded UP (kernels.cuh:disp_level_fast)
     vp.inv100_a = nextafterf((float)(100.0 / c->geo.a), INFINITY);
     vp.lev_slack = nextafterf((float)(2e-4 / c->geo.a), INFINITY);
@@ -1667,10 +1687,11 @@ static int update_activity(misa_b200_ctx *c) {
 }
 
 // NewtonMotion::firststep + the displacement test of atom::decide, enqueued on the main stream
-static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false) {
+static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false, bool push = false) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
     VerletPar vp = verlet_par(c);
+    vp.push = push ? c->d_p2p_dev : nullptr;   // band sites store their new position straight into the neighbours' ghosts
     Slot sl(c, MISA_B200_K_VERLET1);
     c->mark_valid = false;
     if (c->opt_mark && c->opt_prune) {   // this step's marks carry a fresh epoch byte (1..255): nothing to clear
@@ -1680,8 +1701,10 @@ static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false) {
         c->mark_valid = true;
     }
     CU(cudaMemsetAsync(c->d_stepinfo, 0, 3 * sizeof(unsigned long long) + sizeof(int), c->stream));   // [0..2] + counters[0] (run-aways)
-    if (kick2) k_verlet1<true><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
-    else k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
+#define V1(K, P) k_verlet1<K, P><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo)
+    if (vp.push) { if (kick2) V1(true, true); else V1(false, true); }
+    else { if (kick2) V1(true, false); else V1(false, false); }
+#undef V1
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -1785,6 +1808,15 @@ static bool pipe_ok(const misa_b200_ctx *c) {
     return c->opt_pipe && c->opt_fast && c->opt_prune && c->opt_fuse && c->tex_all && !has_inter(c) && !c->inter_active &&
            c->stream2 && make_plan(c, sp, sb);
 }
+// The ghost pushes of the sync-free step done from INSIDE the producing kernels (k_verlet1: positions, k_rho_f's epilogue: df),
+// ARRIVE posted by the consuming stencil kernel's first CTA: needs the third-generation kernels on both stencil launches.
+static bool fused_ok(const misa_b200_ctx *c) {
+    StagePlan sp;
+    size_t sb;
+    if (!c->opt_push_fused || !c->opt_dmax_flags || !c->d_p2p_dev || !c->opt_fast || !c->tex_all || !make_plan(c, sp, sb)) return false;
+    if (sym_ok(c, sp, false, StencilOpt())) return false;
+    return sp.single >= 0 || dilute_ok(c, sp, false);
+}
 // kick2_in: the previous step of this call left its second half-kick to this step's k_verlet1<true>;
 // defer_out: the caller runs another step right after this one, so this step may do the same (*deferred says it did).
 static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false, bool defer_out = false, bool *deferred = nullptr) {
@@ -1800,7 +1832,20 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
     // with the direct push (p2p.cuh) an exchange costs tens of microseconds: nothing left to hide
     const bool p2p = c->p2p_active && c->opt_p2p;
     const bool overlap = c->opt_overlap > 1 || (c->opt_overlap == 1 && nccl_dims >= 1) || (c->opt_overlap < 0 && nccl_dims >= 2 && !p2p);
-    TRY(verlet1_enqueue(c, kick2_in));
+    const bool fused = p2p && !overlap && c->stream2 && fused_ok(c);
+    unsigned long long e_x = 0, e_df = 0;
+    if (fused) {
+        // READY for both exchanges of this step (unless the previous step of this call sent it ahead), then the gate: every
+        // destination has freed its ghosts -- k_verlet1 and k_rho_f store into them without a look at the flags
+        e_x = c->p2p_epoch + 1; e_df = c->p2p_epoch + 2;
+        const unsigned long long post = c->p2p_ready_sent < e_df ? e_df : 0ULL;
+        c->p2p.fence_mode = c->opt_p2p_fence;
+        k_p2p_ready_gate<<<1, 32, 0, c->stream>>>(c->p2p, post, e_df, c->d_flags, c->d_p2p_err);
+        c->launches++;
+        CU(cudaGetLastError());
+        c->p2p_ready_sent = std::max(c->p2p_ready_sent, e_df);
+    }
+    TRY(verlet1_enqueue(c, kick2_in, fused));
     StencilOpt whole, interior, boundary;
     whole.dmax2 = c->d_stepinfo_g + 1;
     interior.region = 1; interior.dmax2 = c->d_stepinfo + 1; interior.reserve_sms = c->opt_reserve;
@@ -1817,12 +1862,24 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
             TRY(activity_enqueue(c, c->stream2));
             CU(cudaEventRecord(c->ev_act, c->stream2));
             c->dmax_by_flags = c->opt_dmax_flags != 0;
-            { Slot sl(c, MISA_B200_K_HALO_X); TRY(p2p_push(c, true, c->stream)); }
-            if (!c->dmax_by_flags) CU(cudaStreamWaitEvent(c->stream, c->ev_act, 0));
             whole.late = true;                      // the wait for the neighbours' pushes moves into the stencil kernels
-            TRY(launch_rho(c, true, false, whole));
-            { Slot sl(c, MISA_B200_K_HALO_DF); TRY(p2p_push(c, false, c->stream)); }
-            TRY(launch_force(c, false, whole));
+            if (fused) {
+                // k_verlet1 has stored the band sites' positions into the neighbours' ghosts; rho's first CTA posts ARRIVE
+                // (+ this sub-box's displacement maximum), its epilogue pushes df; force's first CTA posts that ARRIVE
+                whole.fused = true;
+                c->p2p_epoch = e_x;
+                whole.post_epoch = e_x; whole.post_dmax = c->d_stepinfo + 1;
+                TRY(launch_rho(c, true, false, whole));
+                c->p2p_epoch = e_df;
+                whole.post_epoch = e_df; whole.post_dmax = nullptr;
+                TRY(launch_force(c, false, whole));
+            } else {
+                { Slot sl(c, MISA_B200_K_HALO_X); TRY(p2p_push(c, true, c->stream)); }
+                if (!c->dmax_by_flags) CU(cudaStreamWaitEvent(c->stream, c->ev_act, 0));
+                TRY(launch_rho(c, true, false, whole));
+                { Slot sl(c, MISA_B200_K_HALO_DF); TRY(p2p_push(c, false, c->stream)); }
+                TRY(launch_force(c, false, whole));
+            }
             c->dmax_by_flags = false;
         } else {
             TRY(activity_enqueue(c, c->stream));
@@ -1834,7 +1891,7 @@ static int step_pipelined(misa_b200_ctx *c, bool &redone, bool kick2_in = false,
         }
         // ghost x and df are free for the next step's two exchanges -- only when that step follows inside this call:
         // between calls the host may run readers of the ghosts (thermo, dump) that a neighbour's next push must not overtake
-        if (defer_out) TRY(p2p_post_ready(c, 2, c->stream));
+        if (defer_out && !fused) TRY(p2p_post_ready(c, 2, c->stream));   // (fused: the next step's gate kernel posts it)
     } else {
         CU(cudaEventRecord(c->ev_v1, c->stream));
         CU(cudaStreamWaitEvent(c->stream2, c->ev_v1, 0));

@@ -29,14 +29,44 @@
 // ghosts and does not signal ARRIVE -- the neighbour may still be reading them -- so rank skew beyond the limit is an
 // error on every rank concerned, never a data race.
 
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+
+// definition of kernels.cuh:push_site (P2pPeers is complete here)
+template <int NF>
+__device__ __noinline__ void push_site(const P2pPeers *__restrict__ pp, const int d, const int cx, const int y, const int z, const int nx, const int ny,
+                                       const int nz, const int gx, const int gy, const int gz, const int sxc, const int sy, const int field0,
+                                       const double v0, const double v1, const double v2) {
+    // per dimension: bit 0 = low band (s = +1), bit 1 = high band (s = -1); s = 0 always
+    const int bx = (cx < gx ? 1 : 0) | (cx >= nx - gx ? 2 : 0), by = (y < gy ? 1 : 0) | (y >= ny - gy ? 2 : 0), bz = (z < gz ? 1 : 0) | (z >= nz - gz ? 2 : 0);
+    const long long stride = pp->stride;
+    if (*pp->fault) return;   // the gate in front of this kernel gave up on a neighbour's READY: store nothing (p2p_check reports it)
+    for (int iz = 0; iz < 3; iz++) {
+        if (iz && !((bz >> (iz - 1)) & 1)) continue;
+        const int sz_ = iz == 0 ? 0 : (iz == 1 ? 1 : -1);
+        for (int iy = 0; iy < 3; iy++) {
+            if (iy && !((by >> (iy - 1)) & 1)) continue;
+            const int sy_ = iy == 0 ? 0 : (iy == 1 ? 1 : -1);
+            for (int ix = 0; ix < 3; ix++) {
+                if (ix && !((bx >> (ix - 1)) & 1)) continue;
+                const int sx_ = ix == 0 ? 0 : (ix == 1 ? 1 : -1);
+                if (!(sx_ | sy_ | sz_)) continue;
+                const int k = (sx_ + 1) + 3 * (sy_ + 1) + 9 * (sz_ + 1);
+                const long long b = (long long)d + sx_ * nx + ((long long)sz_ * nz * sy + (long long)sy_ * ny) * sxc;
+                double *P = pp->xyzd[k] + (long long)field0 * stride + b;
+                if (NF == 3) {
+                    double x = v0, yy = v1, zz = v2;
+                    if (pp->shift[k][0] != 0.0) x = __dadd_rn(x, pp->shift[k][0]);
+                    if (pp->shift[k][1] != 0.0) yy = __dadd_rn(yy, pp->shift[k][1]);
+                    if (pp->shift[k][2] != 0.0) zz = __dadd_rn(zz, pp->shift[k][2]);
+                    P[0] = x; P[stride] = yy; P[2 * stride] = zz;
+                } else {
+                    P[0] = v0;
+                }
+            }
+        }
+    }
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
+template __device__ void push_site<3>(const P2pPeers *, int, int, int, int, int, int, int, int, int, int, int, int, int, double, double, double);
+template __device__ void push_site<1>(const P2pPeers *, int, int, int, int, int, int, int, int, int, int, int, int, int, double, double, double);
 
 // code k = (sx+1) + 3 (sy+1) + 9 (sz+1): the ORIGIN of my ghosts with that code sits at sub-box offset +s from me; I push my
 // own group k to the sub-box at offset -s. Thread k handles direction k.
@@ -47,6 +77,16 @@ __device__ __forceinline__ bool p2p_wait(const unsigned long long *w, const unsi
         if (clock64() - t0 > limit) { *(volatile unsigned int *)err = what; return false; }
     return true;
 }
+// READY posted for `epoch_post` (0: nothing to post), then wait until every destination has freed its ghosts up to `epoch_wait`:
+// the gate in front of a producing kernel that pushes from inside (k_verlet1 with VerletPar::push, k_rho_f with a df push)
+__global__ void k_p2p_ready_gate(const P2pPeers pp, const unsigned long long epoch_post, const unsigned long long epoch_wait,
+                                 const unsigned long long *__restrict__ my_flags, unsigned int *__restrict__ err) {
+    const int k = threadIdx.x;
+    if (k >= 27 || !((pp.mask >> k) & 1u)) return;
+    if (epoch_post) { __threadfence_system(); st_release_sys(pp.flags[26 - k] + P2P_READY + k, epoch_post); }
+    if (!p2p_wait(my_flags + P2P_READY + k, epoch_wait, err, 1u + k, pp.spin_limit)) *pp.fault = 1u;
+}
+
 // READY: I am receiver for code k -> tell its origin, which is my destination for code 26 - k, that everything enqueued
 // before this kernel (the readers of my ghosts) is done. `epoch` may lie ahead: "free up to and including exchange epoch".
 __global__ void k_p2p_ready(const P2pPeers pp, const unsigned long long epoch) {
@@ -285,6 +325,14 @@ static int p2p_setup(misa_b200_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(d_ok);
     if (!ok) { p2p_release(c); return 0; }
+    // device copy of the peer table for the kernels that push from inside (k_verlet1, k_rho_f)
+    if (!c->d_p2p_fault) TRY(dmalloc(&c->d_p2p_fault, 1));
+    CU(cudaMemsetAsync(c->d_p2p_fault, 0, sizeof(unsigned int), c->stream));
+    pp.fault = c->d_p2p_fault;
+    pp.fence_mode = c->opt_p2p_fence;
+    if (!c->d_p2p_dev) TRY(dmalloc(&c->d_p2p_dev, 1));
+    CU(cudaMemcpyAsync(c->d_p2p_dev, &pp, sizeof pp, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     c->p2p_active = true;
     c->p2p_epoch = 0;
     c->p2p_ready_sent = 0;

@@ -14,14 +14,14 @@ torch = pytest.importorskip("torch")
 import torch.multiprocessing as mp
 
 
-def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka, opts=""):
+def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka, opts="", vacancies=0):
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     if opts:
         os.environ["MISA_B200_OPTS"] = opts
     lib = mb.load()
     mb.capi._ck(lib.misa_b200_env_init(rank))
     coord = (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
-    st = cm.make_state(phase, ratio=ratio, sigma=0.03)
+    st = cm.make_state(phase, ratio=ratio, sigma=0.03, vacancies=vacancies)
     ctx = cm.gpu_context(st, grid=grid, coord=coord, dt=pka["dt"] if pka else 0.001)
     uid_path = os.path.join(out_dir, "uid.bin")
     if rank == 0:
@@ -46,12 +46,12 @@ def _worker(rank, world, phase, grid, ratio, steps, out_dir, pka, opts=""):
     ctx.close()
 
 
-def _run(tmp_path, phase, grid, ratio, steps, pka=None, opts=""):
+def _run(tmp_path, phase, grid, ratio, steps, pka=None, opts="", vacancies=0):
     world = grid[0] * grid[1] * grid[2]
     if mb.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    mp.spawn(_worker, args=(world, phase, grid, ratio, steps, str(tmp_path), pka, opts), nprocs=world, join=True)
-    st = cm.make_state(phase, ratio=ratio, sigma=0.03)
+    mp.spawn(_worker, args=(world, phase, grid, ratio, steps, str(tmp_path), pka, opts, vacancies), nprocs=world, join=True)
+    st = cm.make_state(phase, ratio=ratio, sigma=0.03, vacancies=vacancies)
     w = cm.oracle_world(st, grid=grid, dt=pka["dt"] if pka else 0.001, threads=world)
     w.prepare()
     if pka:
@@ -134,6 +134,29 @@ def test_two_gpus_wait_for_the_push_inside_the_stencil_kernels(tmp_path):
     for r in range(2):
         for fld in ("type", "x", "v", "f", "rho", "df"):
             assert np.array_equal(out["late"][r][fld], out["front"][r][fld]), (r, fld)
+
+
+@pytest.mark.parametrize("phase,ratio,vacancies", [((80, 8, 8), (1, 0, 0), 0), ((24, 10, 8), (97, 2, 1), 0), ((16, 8, 10), (1, 0, 0), 4)])
+def test_two_gpus_push_from_inside_the_producers_equals_the_push_kernels(tmp_path, phase, ratio, vacancies):
+    """The sync-free step's ghost pushes done by k_verlet1 (positions) and k_rho_f's epilogue (df), ARRIVE posted by the
+    consuming stencil kernel (or a tiny kernel when it cannot wait inside: vacancies), against the push kernels of
+    csrc/p2p.cuh: the ghosts get the same bits, so every field of the trajectory is identical -- and both track the oracle.
+    Pure Fe with an interior, the dilute alloy of BASELINE config 3, pure Fe with vacancies."""
+    out = {}
+    for name, opts in (("fused", ""), ("kernels", "push_fused=0")):
+        d = tmp_path / name
+        d.mkdir()
+        w = _run(d, phase, (2, 1, 1), ratio, steps=6, opts=opts, vacancies=vacancies)
+        _compare(d, w, 1e-12, 1e-9)
+        w.close()
+        out[name] = [np.load(os.path.join(str(d), "lat%d.npy" % r)) for r in range(2)]
+        flags = [np.load(os.path.join(str(d), "p2p%d.npy" % r)) for r in range(2)]
+        assert all(f[1] == 0 for f in flags)
+        if flags[0][0] != 1:
+            pytest.skip("no peer access between the two GPUs: the NCCL path ran")
+    for r in range(2):
+        for fld in ("type", "x", "v", "f", "rho", "df"):
+            assert np.array_equal(out["fused"][r][fld], out["kernels"][r][fld]), (r, fld)
 
 
 def test_two_gpus_pka_migrates_across_sub_boxes(tmp_path):

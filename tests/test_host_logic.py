@@ -271,3 +271,32 @@ def test_unit_order_is_a_bijection_with_the_interior_first(phase, which):
         assert all(k < split for _, k in seen[:2 * split]) and all(k >= split for _, k in seen[2 * split:])
     else:
         assert seen == [(p, k) for p in range(2) for k in range(units)]
+
+
+@pytest.mark.parametrize("cells", [(12, 8, 10), (6, 6, 6), (40, 7, 9), (5, 6, 7)])
+def test_arithmetic_push_of_the_fused_kernels_equals_the_composed_map(cells):
+    """kernels.cuh:push_site (positions pushed from inside k_verlet1, df from k_rho_f's epilogue) derives a band site's
+    destinations arithmetically: per dimension stay, or +n cells from the low band (origin code +1), -n from the high band
+    (code -1). That map must be misa_b200_plan_push's -- the composition of the reference's three staged exchanges
+    (src/pack/lat_particle_packer.cpp:97-139) -- entry for entry, sub-boxes thinner than two ghost widths included."""
+    dom = capi.make_domain(cells, (1, 1, 1), (0, 0, 0), A, CRF)
+    dst, src, code, _ = capi.plan_push(dom)
+    n = [int(v) for v in dom.sub_box_lattice_size]
+    g = [int(v) for v in dom.lattice_size_ghost]
+    sxc, sy, sz = n[0] + 2 * g[0], n[1] + 2 * g[1], n[2] + 2 * g[2]
+    H = sxc * sy * sz
+    to_dev = lambda idx: (idx >> 1) + (idx & 1) * H
+    want = set(zip(to_dev(src).tolist(), code.tolist(), to_dev(dst).tolist()))
+    got = set()
+    opts = lambda c, nn, gg: [0] + ([1] if c < gg else []) + ([-1] if c >= nn - gg else [])
+    for par in range(2):
+        for z in range(n[2]):
+            for y in range(n[1]):
+                for cx in range(n[0]):
+                    d = par * H + ((z + g[2]) * sy + (y + g[1])) * sxc + cx + g[0]
+                    for s2 in opts(z, n[2], g[2]):
+                        for s1 in opts(y, n[1], g[1]):
+                            for s0 in opts(cx, n[0], g[0]):
+                                if s0 or s1 or s2:
+                                    got.add((d, (s0 + 1) + 3 * (s1 + 1) + 9 * (s2 + 1), d + s0 * n[0] + (s2 * n[2] * sy + s1 * n[1]) * sxc))
+    assert got == want
