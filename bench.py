@@ -578,8 +578,10 @@ def run_b200(args):
     e2e_s = env.reduce(time.perf_counter() - t0, "max")
     e2e = {"value": n_gpus * atoms_per_gpu * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ctx.n_owned * 104,
            "d2h_bytes_per_step": ctx.n_owned * 104, "steps": e2e_steps,
-           "api": "misa_b200_step_host(ctx, AtomElement* host, 1): upload the owned box of the host AoS array (pitched 3-D copy "
-                  "from page-locked memory), one step, download the owned box"}
+           "api": "misa_b200_step_host(ctx, AtomElement* host, 1): the owned box of the host AoS array (page-locked) goes up, one step runs, "
+                  "the owned box comes back -- all 104-byte records both ways; on one sub-box as z-slabs on two copy streams with the "
+                  "step's kernels running slab by slab between them (csrc/misa_b200.cu:step_host_slabs)",
+           "slab_pipelined_steps": int(ctx.query("host_slab_steps")), "slab_redone": int(ctx.query("host_slab_redo"))}
     # the three reference hooks on the host array (EAM part of a step only; what the unmodified driver calls)
     t0 = time.perf_counter()
     for _ in range(3):

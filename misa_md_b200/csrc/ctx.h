@@ -152,6 +152,19 @@ struct misa_b200_ctx {
     int n_ghost_map = 0;                  // fused periodic ghost fill (all_self only)
     int *d_ghost_dst = nullptr, *d_ghost_src = nullptr;
     int8_t *d_ghost_shift = nullptr;      // per ghost site: shift code (3 x {-1,0,1}) packed
+    std::vector<int> h_ghost_dst, h_ghost_src;   // host copies of the fused fill map (all_self), for the per-slab sub-maps below
+    std::vector<int8_t> h_ghost_code;
+    // slab-pipelined misa_b200_step_host (misa_b200.cu:step_host_slabs): z-slabs of the owned box travel H2D / D2H on two copy
+    // streams while earlier / later slabs are being computed; the fill map re-sorted by the SOURCE site's slab
+    int opt_host_slabs = 1, slab_T = 3;
+    int n_slabs = 0;
+    std::vector<int> slab_z0, slab_map_ofs;      // [n_slabs + 1]
+    int *d_slab_dst = nullptr, *d_slab_src = nullptr;
+    int8_t *d_slab_code = nullptr;
+    unsigned char *d_aos_out = nullptr;          // second staging array: the input records stay intact until the step is known to be good
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_out;
+    int64_t host_slab_steps = 0, host_slab_redo = 0;
     double *d_sendbuf[2] = {nullptr, nullptr}, *d_recvbuf[2] = {nullptr, nullptr};
     size_t halo_buf_elems = 0;
     // direct push of the composed ghost <- owned map into the neighbours' HBM (p2p.cuh)

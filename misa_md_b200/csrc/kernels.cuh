@@ -184,7 +184,8 @@ k_force(const Geo g, const Soa s, const DevTables tb, const int *__restrict__ of
 #define MARK_CAP 4096     // marking atoms per step; beyond it the map is void (stepinfo[2] tells the stencil kernels)
 struct VerletPar { double dt; double c[MISA_MAX_TYPES]; int mark_T; unsigned char *hot; unsigned char epoch; unsigned long long *mark_count;
                    float inv100_a, lev_slack;      // 100 / a and 2e-4 / a, both rounded up (disp_level_fast)
-                   const P2pPeers *push; };        // non-null: band sites store their new position into the neighbours' ghosts (push_site)
+                   const P2pPeers *push;           // non-null: band sites store their new position into the neighbours' ghosts (push_site)
+                   long long c_begin, c_end; };    // owned-cell ordinals [c_begin, c_end) of each sub-lattice this launch covers (a z-slab; default: all)
 // dt / (2 m) of species t WITHOUT indexing the kernel parameter dynamically: `vp.c[t]` made the compiler copy the whole
 // parameter struct to local memory in every thread (9 STL + 1 LDL per atom in the SASS of the round-1 kernels)
 __device__ __forceinline__ double kick_coef(const VerletPar &vp, const int t) { return t == 0 ? vp.c[0] : (t == 1 ? vp.c[1] : vp.c[2]); }
@@ -310,9 +311,9 @@ k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
           int *__restrict__ runaway_sites, const int runaway_cap, unsigned long long *__restrict__ stepinfo) {
     const int p = blockIdx.x >= blocks_per_parity;
     const int b = blockIdx.x - p * blocks_per_parity;
-    const long long c = (long long)b * blockDim.x + threadIdx.x;
+    const long long c = vp.c_begin + (long long)b * blockDim.x + threadIdx.x;
     double dist = 0.0;
-    if (c < g.n_cells_owned) dist = verlet1_site<KICK2, PUSH>(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
+    if (c < vp.c_end) dist = verlet1_site<KICK2, PUSH>(g, s, vp, p, c, counters, runaway_sites, runaway_cap);
     // maximum over the BLOCK first: one look at the running maximum per block, not per warp -- 62 500 volatile reads of one word
     // per launch queue up at a single L2 slice (about one per clock: tens of microseconds of a 60-microsecond kernel)
     __shared__ double wmax[MISA_BLOCK / 32];
@@ -332,8 +333,8 @@ __global__ void __launch_bounds__(MISA_BLOCK)
 k_verlet2(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity) {
     const int p = blockIdx.x >= blocks_per_parity;
     const int b = blockIdx.x - p * blocks_per_parity;
-    const long long c = (long long)b * blockDim.x + threadIdx.x;
-    if (c >= g.n_cells_owned) return;
+    const long long c = vp.c_begin + (long long)b * blockDim.x + threadIdx.x;
+    if (c >= vp.c_end) return;
     int cx, y, z;
     const int d = owned_cell_to_dev(g, p, c, cx, y, z);
     const int t = s.type[d];
@@ -439,8 +440,8 @@ enum { F_ID = 1, F_TYPE = 2, F_X = 4, F_V = 8, F_F = 16, F_RHO = 32, F_DF = 64, 
 
 __global__ void __launch_bounds__(MISA_BLOCK)
 k_aos_to_soa(const long long n_ext, const long long H, const unsigned long long *__restrict__ aos, const Soa s, const int fields,
-             const Geo g = Geo(), const int owned_only = 0) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+             const Geo g = Geo(), const int owned_only = 0, const long long idx0 = 0) {   // records [idx0, n_ext): a z-slab, or everything
+    const long long idx = idx0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_ext) return;
     if (owned_only) {
         const int sx = 2 * g.sxc;
@@ -461,9 +462,10 @@ k_aos_to_soa(const long long n_ext, const long long H, const unsigned long long 
 }
 // owned_only: write back only sites inside the sub-box (ghost records of the host array stay untouched)
 __global__ void __launch_bounds__(MISA_BLOCK)
-k_soa_to_aos(const Geo g, unsigned long long *__restrict__ aos, const Soa s, const int fields, const int owned_only) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.n_ext) return;
+k_soa_to_aos(const Geo g, unsigned long long *__restrict__ aos, const Soa s, const int fields, const int owned_only, const long long idx0 = 0,
+             const long long idx1 = -1) {   // records [idx0, idx1): a z-slab; default everything
+    const long long idx = idx0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (idx1 < 0 ? g.n_ext : idx1)) return;
     if (owned_only) {
         const int sx = 2 * g.sxc;
         const int x = (int)(idx % sx);

@@ -344,6 +344,7 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
         std::vector<int8_t> codes;
         compose_push_map(send, recv, n, dst_list, srcs, codes);
         if (c->all_self) {
+            c->h_ghost_dst = dst_list; c->h_ghost_src = srcs; c->h_ghost_code = codes;
             c->n_ghost_map = (int)dst_list.size();
             TRY(dmalloc(&c->d_ghost_dst, dst_list.size())); TRY(dmalloc(&c->d_ghost_src, dst_list.size())); TRY(dmalloc(&c->d_ghost_shift, dst_list.size()));
             CU(cudaMemcpy(c->d_ghost_dst, dst_list.data(), dst_list.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -397,6 +398,11 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
+    cudaFree(c->d_slab_dst); cudaFree(c->d_slab_src); cudaFree(c->d_slab_code); cudaFree(c->d_aos_out);
+    if (c->s_up) cudaStreamDestroy(c->s_up);
+    if (c->s_dn) cudaStreamDestroy(c->s_dn);
+    for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_out) cudaEventDestroy(e);
     cudaFreeHost(c->h_counters); cudaFree(c->d_reduce); cudaFreeHost(c->h_reduce);
     cudaFree(c->d_minor); cudaFree(c->d_minor_count); cudaFree(c->d_mcount); cudaFree(c->d_mentry);
     cudaFree(c->d_lo_tab); cudaFree(c->d_pair);
@@ -899,6 +905,8 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "dmax_flags")) c->opt_dmax_flags = value;
     else if (!strcmp(name, "p2p_fence")) c->opt_p2p_fence = value;
     else if (!strcmp(name, "push_fused")) c->opt_push_fused = value;
+    else if (!strcmp(name, "host_slabs")) c->opt_host_slabs = value;
+    else if (!strcmp(name, "slab_planes")) { c->slab_T = std::max(3, value); c->n_slabs = 0; }
     else if (!strcmp(name, "p2p_debug")) {
         if (value && !c->d_p2p_dbg) {
             TRY(dmalloc(&c->d_p2p_dbg, 16));
@@ -931,6 +939,8 @@ extern "C" int misa_b200_query(misa_b200_ctx *c, const char *name, double *value
     else if (!strcmp(name, "n_full")) *value = c->n_full;
     else if (!strcmp(name, "pipe_steps")) *value = (double)c->pipe_steps;
     else if (!strcmp(name, "pipe_redo")) *value = (double)c->pipe_redo;
+    else if (!strcmp(name, "host_slab_steps")) *value = (double)c->host_slab_steps;
+    else if (!strcmp(name, "host_slab_redo")) *value = (double)c->host_slab_redo;
     else if (!strcmp(name, "dmax")) *value = c->dmax_valid ? sqrt(c->dmax2) : -1.0;
     else if (!strcmp(name, "single")) *value = planned ? sp.single : -2;
     else if (!strcmp(name, "novac")) *value = no_vacancy(c) ? 1 : 0;
@@ -1294,6 +1304,8 @@ extern "C" int misa_b200_plan_unit_order(const misa_b200_domain *dom, int which,
     *parity = par; *unit = up;
     return MISA_B200_OK;
 }
+struct StencilOpt;
+static RegionList regions_for(const misa_b200_ctx *c, const StencilOpt &so, bool late);
 struct StencilOpt {                 // how one stencil launch deviates from "whole sub-box, host-chosen list, main stream"
     int region = 0;                 // 0 whole, 1 interior, 2 boundary slabs
     const unsigned long long *dmax2 = nullptr;
@@ -1302,7 +1314,17 @@ struct StencilOpt {                 // how one stencil launch deviates from "who
     bool fused = false;             // that push was done from inside the producing kernel: this launch posts its ARRIVE flags (post_epoch,
     unsigned long long post_epoch = 0;   // post_dmax) and, for rho + df, pushes df from its epilogue
     const unsigned long long *post_dmax = nullptr;
+    int z0 = -1, z1 = -1;           // z0 >= 0: only the owned z-planes [z0, z1) (slab-pipelined misa_b200_step_host)
 };
+static RegionList regions_for(const misa_b200_ctx *c, const StencilOpt &so, bool late) {
+    if (so.z0 < 0) return make_regions(c->geo, late ? 3 : so.region);
+    RegionList rl;
+    memset(&rl, 0, sizeof rl);
+    Region &r = rl.r[rl.n++];
+    r.x0 = 0; r.y0 = 0; r.z0 = so.z0; r.nx = c->geo.nx; r.ny = c->geo.ny; r.nz = so.z1 - so.z0; r.u0 = 0;
+    rl.units = ((long long)r.nx * r.ny * r.nz + 31) / 32;
+    return rl;
+}
 // ---- pair-symmetric passes (eam_sym.cuh) --------------------------------------------------------------------------
 // One species (or a dilute alloy, whose main loop is the majority species'), overwrite semantics, the whole sub-box in
 // one launch (the interior / boundary split of the overlapped exchange keeps the full-list kernels).
@@ -1401,7 +1423,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_vacancy(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-        const RegionList rl = make_regions(g, late ? 3 : so.region);
+        const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
         if (sym_ok(c, sp, accum, so)) {
@@ -1453,7 +1475,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         tex.df = c->tex_df;
         const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
         const bool novac = no_vacancy(c);
-        const RegionList rl = make_regions(g, so.region);
+        const RegionList rl = regions_for(c, so, false);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
 #define RHO_S(S, F, A) k_rho_s<S, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
@@ -1560,7 +1582,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
 #else
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
 #endif
-        const RegionList rl = make_regions(g, late ? 3 : so.region);
+        const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         const MinorList ml = minor_list(c);
         if (rl.units > 0) {
@@ -1590,7 +1612,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
 #else
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
 #endif
-        const RegionList rl = make_regions(g, late ? 3 : so.region);
+        const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
 #define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); \
@@ -1608,7 +1630,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         tex.df = c->tex_df;
         const bool use_tex = c->opt_tex && c->tex_x[0] && c->tex_x[1] && c->tex_x[2] && c->tex_df;
         const bool novac = no_vacancy(c);
-        const RegionList rl = make_regions(g, so.region);
+        const RegionList rl = regions_for(c, so, false);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
 #define FORCE_S(S, A) k_force_s<S, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, tex, rl, ls)
@@ -1655,6 +1677,7 @@ static VerletPar verlet_par(const misa_b200_ctx *c) {
     vp.dt = c->dt;
     for (int i = 0; i < MISA_MAX_TYPES; i++) vp.c[i] = c->dt_inv_m[i];
     vp.mark_T = 0; vp.hot = nullptr; vp.epoch = 0; vp.mark_count = nullptr; vp.push = nullptr;
+    vp.c_begin = 0; vp.c_end = c->geo.n_cells_owned;
     // level arithmetic of k_verlet1 in single precision, every constant rounded UP (kernels.cuh:disp_level_fast)
     vp.inv100_a = nextafterf((float)(100.0 / c->geo.a), INFINITY);
     vp.lev_slack = nextafterf((float)(2e-4 / c->geo.a), INFINITY);
@@ -1966,10 +1989,186 @@ extern "C" int misa_b200_step(misa_b200_ctx *c, int n_steps) {
 // halo before they are read, rho / f are cleared (src/atom.cpp:86-146) -- so after the first call (full upload: the
 // species census covers the ghost shell) only the owned box crosses PCIe, as one pitched 3-D copy each way, and the
 // host's ghost records are left as they were.
+// ---- slab-pipelined form of one host-buffer step (single sub-box, thermal case) ------------------------------------------------
+// The serial form is PCIe-bound and uses one direction at a time: H2D 208 MB (3.7 ms at 100^3 cells), step (1.1 ms), D2H 208 MB
+// (3.7 ms). Here the owned box is cut into z-slabs of slab_T planes (>= the stencil reach of 2.5 cells, so a slab depends on its
+// two neighbours only). Uploads run on one copy stream in slab order; as slab k lands it is converted, integrated (k_verlet1 on
+// its cell range) and its ghost images filled (the fill map re-sorted by the source site's slab); rho + df of slab k-1 and force +
+// second half-kick of slab k-2 follow, whose records then go back D2H on a second copy stream -- both PCIe directions busy at
+// once. The periodic wrap (slab 0 needs the last slab) leaves rho of two slabs and force of four for the tail. Partner bound of
+// the stencil pruning: the running maximum of the displacements measured so far -- every partner of slab k lies in slabs k-1 ..
+// k+1, which have been measured when rho(k) is enqueued. The INPUT records stay intact in their own staging array: if an atom
+// turns out to have run away, the state is rebuilt from them and the step redone by the serial path (bit-identical results
+// otherwise: tests/test_gpu_parity.py).
+static int slab_setup(misa_b200_ctx *c) {
+    const Geo &g = c->geo;
+    if (c->n_slabs > 0) return 0;
+    const int T = std::max(3, c->slab_T);
+    int S = g.nz / T;
+    if (S < 6) return -1;
+    std::vector<int> z0(S + 1);
+    for (int k = 0; k < S; k++) z0[k] = k * T;
+    z0[S] = g.nz;                                        // the last slab takes the remainder (T .. 2T-1 planes)
+    // fill map by source slab
+    const size_t n = c->h_ghost_dst.size();
+    std::vector<int> slab_of(n), order(n), ofs(S + 1, 0);
+    const long long plane = (long long)g.sxc * g.sy;
+    for (size_t i = 0; i < n; i++) {
+        const long long rem = c->h_ghost_src[i] % g.H;
+        const int z = (int)(rem / plane) - g.gz;
+        int k = std::min(S - 1, std::max(0, z / T));
+        slab_of[i] = k;
+        ofs[k + 1]++;
+    }
+    for (int k = 0; k < S; k++) ofs[k + 1] += ofs[k];
+    std::vector<int> fill(ofs.begin(), ofs.end() - 1), dst(n), src(n);
+    std::vector<int8_t> code(n);
+    for (size_t i = 0; i < n; i++) { const int q = fill[slab_of[i]]++; dst[q] = c->h_ghost_dst[i]; src[q] = c->h_ghost_src[i]; code[q] = c->h_ghost_code[i]; }
+    cudaFree(c->d_slab_dst); cudaFree(c->d_slab_src); cudaFree(c->d_slab_code);
+    c->d_slab_dst = c->d_slab_src = nullptr; c->d_slab_code = nullptr;
+    TRY(dmalloc(&c->d_slab_dst, n)); TRY(dmalloc(&c->d_slab_src, n)); TRY(dmalloc(&c->d_slab_code, n));
+    CU(cudaMemcpy(c->d_slab_dst, dst.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_slab_src, src.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_slab_code, code.data(), n, cudaMemcpyHostToDevice));
+    if (!c->d_aos_out) {
+        TRY(dmalloc(&c->d_aos_out, (size_t)g.n_ext * 104));
+        CU(cudaMemset(c->d_aos_out, 0, (size_t)g.n_ext * 104));   // the padding word of the records goes out as zeros
+    }
+    if (!c->s_up) { CU(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_dn, cudaStreamNonBlocking)); }
+    while ((int)c->ev_up.size() < S) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_up.push_back(a); c->ev_out.push_back(b);
+    }
+    c->slab_z0 = z0; c->slab_map_ofs = ofs; c->n_slabs = S;
+    return 0;
+}
+// z-planes [z0, z1) of the owned box of a ghost-extended AoS array as one pitched 3-D copy
+static int copy_owned_slab(misa_b200_ctx *c, void *dst, const void *src, cudaMemcpyKind kind, int z0, int z1, cudaStream_t st) {
+    const Geo &g = c->geo;
+    const size_t rec = 104, pitch = 2 * (size_t)g.sxc * rec;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), pitch, pitch, (size_t)g.sy);
+    p.dstPtr = make_cudaPitchedPtr(dst, pitch, pitch, (size_t)g.sy);
+    p.srcPos = p.dstPos = make_cudaPos(2 * (size_t)g.gx * rec, (size_t)g.gy, (size_t)(g.gz + z0));
+    p.extent = make_cudaExtent(2 * (size_t)g.nx * rec, (size_t)g.ny, (size_t)(z1 - z0));
+    p.kind = kind;
+    CU(cudaMemcpy3DAsync(&p, st));
+    return 0;
+}
+static bool host_slabs_ok(misa_b200_ctx *c) {
+    StagePlan sp;
+    size_t sb;
+    if (!c->opt_host_slabs || !c->all_self || c->comm_size != 1 || c->n_ghost_map <= 0 || c->h_ghost_dst.empty() || c->prof_on) return false;
+    if (!pipe_ok(c) || !make_plan(c, sp, sb) || sp.single < 0 || !c->dmax_valid) return false;   // thermal, single species (the minority-atom launch of dilute alloys is per box)
+    return slab_setup(c) == 0;
+}
+static int step_host_slabs(misa_b200_ctx *c, void *atoms, bool &redo) {
+    const Geo &g = c->geo;
+    const int S = c->n_slabs;
+    const long long row = 2LL * g.sxc, plane_recs = row * g.sy, cells_plane = (long long)g.nx * g.ny;
+    redo = false;
+    // the step's words, marks: as verlet1_enqueue
+    VerletPar vp = verlet_par(c);
+    c->mark_valid = false;
+    if (c->opt_mark && c->opt_prune) {
+        c->mark_epoch = c->mark_epoch % 255 + 1;
+        c->mark_T_used = c->mark_T_next;
+        vp.mark_T = c->mark_T_used; vp.hot = c->d_hot; vp.epoch = (unsigned char)c->mark_epoch; vp.mark_count = c->d_stepinfo + 2;
+        c->mark_valid = true;
+    }
+    CU(cudaMemsetAsync(c->d_stepinfo, 0, 3 * sizeof(unsigned long long) + sizeof(int), c->stream));
+    CU(cudaEventRecord(c->ev_v1, c->stream));
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_v1, 0));          // uploads may not overtake whatever the previous call left on the main stream
+    CU(cudaStreamWaitEvent(c->s_dn, c->ev_v1, 0));
+    for (int k = 0; k < S; k++) {
+        TRY(copy_owned_slab(c, c->d_aos, atoms, cudaMemcpyHostToDevice, c->slab_z0[k], c->slab_z0[k + 1], c->s_up));
+        CU(cudaEventRecord(c->ev_up[k], c->s_up));
+    }
+    StencilOpt so;
+    so.dmax2 = c->d_stepinfo + 1;                           // running maximum over the slabs integrated so far
+    auto slab_in = [&](int k) -> int {                      // records -> SoA, first half-kick + drift, ghost images of the slab's sites
+        const int z0 = c->slab_z0[k], z1 = c->slab_z0[k + 1];
+        CU(cudaStreamWaitEvent(c->stream, c->ev_up[k], 0));
+        const long long i0 = (long long)(g.gz + z0) * plane_recs, i1 = (long long)(g.gz + z1) * plane_recs;
+        k_aos_to_soa<<<nblk(i1 - i0), MISA_BLOCK, 0, c->stream>>>(i1, g.H, (const unsigned long long *)c->d_aos, c->s, F_X | F_V | F_F, g, 1, i0);
+        VerletPar v = vp;
+        v.c_begin = z0 * cells_plane; v.c_end = z1 * cells_plane;
+        const int bpp = nblk(v.c_end - v.c_begin);
+        k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, v, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
+        const int m0 = c->slab_map_ofs[k], m = c->slab_map_ofs[k + 1] - m0;
+        if (m > 0)
+            k_ghost_fill_x<<<nblk(m), MISA_BLOCK, 0, c->stream>>>(m, c->d_slab_dst + m0, c->d_slab_src + m0, c->d_slab_code + m0, c->s, c->dom.meas_global_length[0],
+                                                               c->dom.meas_global_length[1], c->dom.meas_global_length[2]);
+        c->launches += 3;
+        CU(cudaGetLastError());
+        return 0;
+    };
+    auto slab_rho = [&](int k) -> int {
+        so.z0 = c->slab_z0[k]; so.z1 = c->slab_z0[k + 1];
+        TRY(launch_rho(c, true, false, so));
+        const int m0 = c->slab_map_ofs[k], m = c->slab_map_ofs[k + 1] - m0;
+        if (m > 0) { k_ghost_fill_1<<<nblk(m), MISA_BLOCK, 0, c->stream>>>(m, c->d_slab_dst + m0, c->d_slab_src + m0, c->s.df); c->launches++; }
+        CU(cudaGetLastError());
+        return 0;
+    };
+    auto slab_out = [&](int k) -> int {                     // force, second half-kick, SoA -> records, D2H
+        const int z0 = c->slab_z0[k], z1 = c->slab_z0[k + 1];
+        so.z0 = z0; so.z1 = z1;
+        TRY(launch_force(c, false, so));
+        VerletPar v = vp;
+        v.c_begin = z0 * cells_plane; v.c_end = z1 * cells_plane;
+        const int bpp = nblk(v.c_end - v.c_begin);
+        k_verlet2<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, v, bpp);
+        const long long i0 = (long long)(g.gz + z0) * plane_recs, i1 = (long long)(g.gz + z1) * plane_recs;
+        k_soa_to_aos<<<nblk(i1 - i0), MISA_BLOCK, 0, c->stream>>>(g, (unsigned long long *)c->d_aos_out, c->s, F_ALL, 1, i0, i1);
+        c->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev_out[k], c->stream));
+        CU(cudaStreamWaitEvent(c->s_dn, c->ev_out[k], 0));
+        return copy_owned_slab(c, atoms, c->d_aos_out, cudaMemcpyDeviceToHost, z0, z1, c->s_dn);
+    };
+    for (int k = 0; k < S; k++) {
+        TRY(slab_in(k));
+        if (k >= 2) TRY(slab_rho(k - 1));                   // slabs k-2, k-1, k are in
+        if (k >= 4) TRY(slab_out(k - 2));                   // rho of k-3, k-2, k-1 is done
+    }
+    TRY(slab_rho(S - 1));
+    TRY(slab_rho(0));
+    for (int k : {S - 2, S - 1, 0, 1}) TRY(slab_out(k));
+    TRY(activity_enqueue(c, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->s_dn));
+    c->inter_active = c->h_stepinfo[0] > 0;
+    c->host_slab_steps++;
+    if (c->inter_active || c->h_counters[3] != 0) {
+        // something ran away: the records that just went back are void. Rebuild the state from the intact input records and let
+        // the caller redo the step through the serial path (decide, inter-atom lists).
+        c->host_slab_redo++;
+        k_aos_to_soa<<<nblk(g.n_ext), MISA_BLOCK, 0, c->stream>>>(g.n_ext, g.H, (const unsigned long long *)c->d_aos, c->s, F_X | F_V | F_F, g, 1);
+        c->launches++;
+        CU(cudaGetLastError());
+        c->inter_active = false;
+        redo = true;
+        return 0;
+    }
+    TRY(verlet1_finish(c));
+    return 0;
+}
+
 extern "C" int misa_b200_step_host(misa_b200_ctx *c, void *atoms, int n_steps) {
     REQ(c && atoms, MISA_B200_EINVAL, "misa_b200_step_host: null argument");
     REQ(c->have_off && c->have_pot, MISA_B200_ESTATE, "misa_b200_step_host: offsets / potential not set");
     const bool first = !c->census_valid || !c->have_atoms;
+    if (!first && n_steps == 1 && host_slabs_ok(c)) {
+        bool redo = false;
+        TRY(step_host_slabs(c, atoms, redo));
+        if (!redo) return 0;
+        // the state is the caller's input again (rebuilt on the device): serial step + download
+        TRY(misa_b200_step(c, 1));
+        return d2h_aos(c, atoms, F_ALL, 2);
+    }
     TRY(h2d_aos(c, atoms, F_ALL, first ? 0 : 1));
     if (!c->census_valid) { TRY(census_local(c)); TRY(census_fetch(c)); }
     c->have_atoms = true;

@@ -381,6 +381,50 @@ def test_step_host_moves_only_the_owned_box_and_equals_resident_steps():
     ctx.close()
 
 
+@pytest.mark.parametrize("planes", [4, 3])
+def test_step_host_slab_pipeline_equals_resident_steps_and_falls_back_on_a_runaway(planes):
+    """The slab-pipelined misa_b200_step_host (z-slabs uploaded, computed and downloaded concurrently, both PCIe directions at
+    once) gives the trajectory of resident stepping bit for bit, owned records only; when an atom runs away inside such a
+    step the input records are restored on the device and the step is redone through the serial path -- same state as
+    resident stepping through the cascade (occupancy, ids, inter-atom list)."""
+    st = cm.make_state((10, 9, 26), sigma=0.04)
+    ref = cm.gpu_context(st)
+    ref.prepare()
+    ctx = cm.gpu_context(st)
+    ctx.set_option("slab_planes", planes)
+    ctx.prepare()
+    host = ctx.download()
+    ctx.host_register(host)
+    ctx.step_host(host, 1)
+    ref.step(1)
+    for _ in range(4):
+        ctx.step_host(host, 1)
+        ref.step(1)
+    assert ctx.query("host_slab_steps") == 5 and ctx.query("host_slab_redo") == 0
+    want = cm.owned(ref, ref.download())
+    got = cm.owned(ctx, host)
+    for fld in ("type", "id", "x", "v", "f", "rho", "df"):
+        assert np.array_equal(got[fld], want[fld]), fld
+    # kick one atom hard enough to leave its site within a few steps: both contexts from the same (bit-identical) state
+    lat, direction = (5, 4, 13, 0), (1.0, 2.0, 3.0)
+    ctx.setv(lat, direction, 300.0)
+    ref.setv(lat, direction, 300.0)
+    host = ctx.download(host)
+    for _ in range(12):
+        ctx.step_host(host, 1)
+        ref.step(1)
+    assert ref.thermo()["n_inter"] > 0 and ctx.query("host_slab_redo") >= 1
+    want = cm.owned(ref, ref.download())
+    got = cm.owned(ctx, host)
+    for fld in ("type", "id", "x", "v", "f", "rho", "df"):
+        assert np.array_equal(got[fld], want[fld]), fld
+    a, b = ctx.download_inter(), ref.download_inter()
+    assert len(a) == len(b) and np.array_equal(a["id"], b["id"]) and np.array_equal(a["x"], b["x"])
+    ctx.host_unregister(host)
+    ctx.close()
+    ref.close()
+
+
 def test_hot_cell_marks_bound_the_partner_rigorously():
     """Per-warp stencil prefixes bound the partner atom by the marking level T unless an atom above T sits within reach
     (k_verlet1 marks those cells). One atom 0.19a off its site, a partner in its <311>/2 shell (2.18a) 0.04a towards it:

@@ -1,0 +1,2 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -30 > gpurun_out/r02n_pytest_parity.log
