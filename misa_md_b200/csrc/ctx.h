@@ -98,6 +98,8 @@ struct misa_b200_ctx {
     unsigned char *d_hot = nullptr, *d_hot_init = nullptr;
     int opt_mark = 1, mark_T_next = 0, mark_T_used = 0, mark_epoch = 0;   // d_hot: epoch bytes; d_hot_init: static edge map
     bool mark_valid = false;
+    unsigned char *d_pmax = nullptr, *d_ptmp = nullptr;   // per-cell partner bound of the serial path (kernels.cuh:k_pmax_*)
+    bool pmax_valid = false;
     int level_n[kLevels] = {0};
     int level_near[kLevels] = {0};        // leading entries (lists are sorted by site distance) that are almost surely in range
     int near_full = 0;
@@ -195,6 +197,7 @@ struct misa_b200_ctx {
     // run-away / inter atoms
     InterSoa inter{};
     int inter_cap = 0;
+    int opt_inter_dev = 1;                // the inter-atom list lives on the device (inter_dev.cuh); 0: host list (inter.cuh)
     int *d_counters = nullptr;            // [0] run-aways this step, [1] n_local inter, [2] n_ghost inter, [3] overflow, [4] invariant violations
     int *h_counters = nullptr;            // pinned, mapped mirror (hd_*: the device's view; k_activity stores into it)
     int *hd_counters = nullptr;

@@ -311,8 +311,7 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
         const int ti = s.type[d];
         const int *off = s_off + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
-                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
+        const int n_off = warp_list_len(ls, lg, hot_ok, d, d - (par ? ls.H : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double acc = 0.0;
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
@@ -445,8 +444,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         const int ti = s.type[d];
         const int tic = max(ti, 0);
         const int *off = s_off + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
-                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
+        const int n_off = warp_list_len(ls, lg, hot_ok, d, d - (par ? ls.H : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         unsigned long long d_eli = 0;
         if (!SINGLE && EAM_MULTI_GENERIC) d_eli = dir[tic];
@@ -745,8 +743,7 @@ k_stencil_stats(const Geo g, const Soa s, const int *__restrict__ offs, const in
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);
         const int *off = offs + (par ? n_list : 0);
-        const int n_off = list_len(ls, lg, __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0),
-                                   __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, d - (par ? ls.H : 0)) : true));
+        const int n_off = warp_list_len(ls, lg, hot_ok, d, d - (par ? ls.H : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         for (int q = 0; q < n_off; q++) {
             const int j = d + off[q];

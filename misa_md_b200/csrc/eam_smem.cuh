@@ -245,6 +245,8 @@ struct LevelSel {
     const unsigned long long *hot_count;    // atoms that marked (or wanted to) this step; above MARK_CAP the map is incomplete
     int hot_T, hot_epoch;
     long long H;
+    // serial path: per-cell partner bound (kernels.cuh:k_pmax_*), takes precedence over the marks
+    const unsigned char *pmax;
 };
 __device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs, int &n_off, int &n_near) {
     if (!ls.dmax2_bits) return;
@@ -264,10 +266,21 @@ __device__ __forceinline__ int base_level(const LevelSel &ls) {
 }
 // offsets a warp loops: lw = largest displacement level among its own atoms (warp-uniform)
 __device__ __forceinline__ bool hot_map_usable(const LevelSel &ls) { return ls.hot && *ls.hot_count <= MARK_CAP; }
-__device__ __forceinline__ bool cell_hot(const LevelSel &ls, const long long cell) { return ls.hot[cell] == ls.hot_epoch || ls.edge[cell] != 0; }
+// (edge == null: the marks were stamped by ghost atoms too -- k_mark_levels -- so cells next to the shell need no special case)
+__device__ __forceinline__ bool cell_hot(const LevelSel &ls, const long long cell) { return ls.hot[cell] == ls.hot_epoch || (ls.edge && ls.edge[cell] != 0); }
 __device__ __forceinline__ int list_len(const LevelSel &ls, const int lg, const int lw, const bool hot) {
     const int L = lw + (hot ? lg : min(lg, ls.hot_T));
     return (lg >= 0 && L < EAM_PAIR_LEVELS) ? ls.prefix[L] : ls.n_full;
+}
+// the prefix a warp loops: lg / hot_ok are the launch's global level and "is the mark map complete"; d = the lane's site, cell
+// = its cell (both sub-lattices share the per-cell maps)
+__device__ __forceinline__ int warp_list_len(const LevelSel &ls, const int lg, const bool hot_ok, const int d, const long long cell) {
+    const int lw = __reduce_max_sync(0xffffffffu, lg >= 0 ? (int)ls.ulev[d] : 0);
+    if (ls.pmax) {
+        const int L = lw + __reduce_max_sync(0xffffffffu, (int)ls.pmax[cell]);
+        return (lg >= 0 && L < EAM_PAIR_LEVELS) ? ls.prefix[L] : ls.n_full;
+    }
+    return list_len(ls, lg, lw, __any_sync(0xffffffffu, hot_ok ? cell_hot(ls, cell) : true));
 }
 
 // ---- neighbour field access: plain global loads (LSU pipe) or texture fetches (TEX pipe of the same L1) -----

@@ -38,6 +38,25 @@ struct InterHost {
 };
 static std::map<misa_b200_ctx *, InterHost *> g_inter_host;
 static InterHost *IH(misa_b200_ctx *c) { return g_inter_host[c]; }
+// device-resident list (inter_dev.cuh, the default: ctx.opt_inter_dev); the functions below keep the host-list form as option
+// "inter_dev" 0 -- the two are tested against each other, bit for bit (tests/test_gpu_inter.py)
+struct VerletPar;
+static int idev_alloc(misa_b200_ctx *c, int cap);
+static void idev_free(misa_b200_ctx *c);
+static int idev_upload(misa_b200_ctx *c, const void *atoms, size_t n);
+static int idev_sync_host(misa_b200_ctx *c);
+static int idev_first_step(misa_b200_ctx *c, const VerletPar &vp);
+static int idev_second_step(misa_b200_ctx *c, const VerletPar &vp);
+static int idev_clear(misa_b200_ctx *c);
+static int idev_scale_v(misa_b200_ctx *c, double fac);
+static int idev_drop_ghosts(misa_b200_ctx *c);
+static int idev_decide(misa_b200_ctx *c);
+static int idev_exchange(misa_b200_ctx *c);
+static int idev_border(misa_b200_ctx *c);
+static int idev_halo_df(misa_b200_ctx *c);
+static int idev_run_pairs(misa_b200_ctx *c, bool force);
+static int idev_thermo(misa_b200_ctx *c, double *d_out);
+static int idev_publish(misa_b200_ctx *c);
 
 // ---- device kernels ---------------------------------------------------------------------------------
 // stepinfo[0] = this sub-box's off-lattice activity (run-aways of this step + listed inter atoms); the caller
@@ -116,11 +135,13 @@ __device__ __forceinline__ bool in_owned(const Geo &g, int x2, int y, int z) {
 template <bool FORCE>
 __global__ void __launch_bounds__(128)
 k_inter_pairs(const Geo g, const Soa s, const DevTables tb, const InterDev in, const int n_local, const int n_total,
-              const int3 *__restrict__ rel, const int n_full, const int *__restrict__ head) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n_total) return;
+              const int3 *__restrict__ rel, const int n_full, const int *__restrict__ head, const int ghost_base = -1) {
+    const int w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w_ >= n_total) return;
+    // list entry of work item w_: ghost copies follow the local atoms directly (host mirror) or start at ghost_base (inter_dev.cuh)
+    const int w = (w_ < n_local || ghost_base < 0) ? w_ : ghost_base + (w_ - n_local);
     const int3 cs = in.cell[w];
-    const bool local = w < n_local;
+    const bool local = w_ < n_local;
     const int ti = in.type[w];
     const double xi = in.x[0][w], yi = in.x[1][w], zi = in.x[2][w];
     const double dfi = FORCE ? in.df[w] : 0.0;
@@ -293,9 +314,10 @@ static int inter_alloc(misa_b200_ctx *c, int cap) {
     CU(cudaMalloc((void **)&b->dv.site, cap * 4)); CU(cudaMalloc((void **)&b->dv.next, cap * 4));
     CU(cudaMalloc((void **)&b->dv.cell, cap * sizeof(int3)));
     (void)g_dummy_rel;
-    return 0;
+    return idev_alloc(c, cap);
 }
 static void inter_free(misa_b200_ctx *c) {
+    idev_free(c);
     InterHost *h = g_inter_host[c];
     InterDevBuf *b = g_inter_dev[c];
     if (h) {
@@ -314,6 +336,7 @@ static void inter_free(misa_b200_ctx *c) {
 }
 
 static int inter_upload(misa_b200_ctx *c, const void *atoms, size_t n) {
+    if (c->opt_inter_dev) return idev_upload(c, atoms, n);
     InterHost *h = IH(c);
     REQ((int)n <= c->inter_cap / 2, MISA_B200_EOVERFLOW, "too many inter atoms");
     h->local.assign((const HostAtom *)atoms, (const HostAtom *)atoms + n);
@@ -325,6 +348,7 @@ static int inter_upload(misa_b200_ctx *c, const void *atoms, size_t n) {
 }
 static int inter_download(misa_b200_ctx *c, void *atoms, size_t cap, size_t *n) {
     InterHost *h = IH(c);
+    if (c->opt_inter_dev) TRY(idev_sync_host(c));
     *n = h->local.size();
     if (atoms) memcpy(atoms, h->local.data(), std::min(cap, *n) * sizeof(HostAtom));
     return 0;
@@ -333,6 +357,7 @@ static int inter_download(misa_b200_ctx *c, void *atoms, size_t cap, size_t *n) 
 // ---- integrator on the list: NewtonMotion::firststep / secondstep inter loops
 //      (reference src/newton_motion.cpp:46-54,68-73); host arithmetic, volatile to forbid contraction ----
 static int inter_first_step(misa_b200_ctx *c, const VerletPar &vp) {
+    if (c->opt_inter_dev) return idev_first_step(c, vp);
     for (HostAtom &a : IH(c)->local)
         for (int d = 0; d < 3; d++) {
             volatile double kick = vp.c[a.type] * a.f[d];
@@ -343,6 +368,7 @@ static int inter_first_step(misa_b200_ctx *c, const VerletPar &vp) {
     return 0;
 }
 static int inter_second_step(misa_b200_ctx *c, const VerletPar &vp) {
+    if (c->opt_inter_dev) return idev_second_step(c, vp);
     for (HostAtom &a : IH(c)->local)
         for (int d = 0; d < 3; d++) {
             volatile double kick = vp.c[a.type] * a.f[d];
@@ -351,15 +377,18 @@ static int inter_second_step(misa_b200_ctx *c, const VerletPar &vp) {
     return 0;
 }
 static void inter_drop_ghosts(misa_b200_ctx *c) {
+    if (c->opt_inter_dev) { idev_drop_ghosts(c); return; }
     IH(c)->ghost.clear();
     for (int i = 0; i < 6; i++) { IH(c)->intersend[i].clear(); IH(c)->interrecv[i].clear(); }
     c->n_inter_ghost = 0;
 }
 static int inter_clear(misa_b200_ctx *c) { // atom::clearForce inter loop, reference src/atom.cpp:94-99
+    if (c->opt_inter_dev) return idev_clear(c);
     for (HostAtom &a : IH(c)->local) { a.f[0] = a.f[1] = a.f[2] = 0; a.rho = 0; }
     return 0;
 }
 static int inter_scale_v(misa_b200_ctx *c, double fac) {
+    if (c->opt_inter_dev) return idev_scale_v(c, fac);
     for (HostAtom &a : IH(c)->local) { a.v[0] *= fac; a.v[1] *= fac; a.v[2] *= fac; }
     return 0;
 }
@@ -382,6 +411,7 @@ static int fetch_sites(misa_b200_ctx *c, const std::vector<int> &dev_sites, std:
 }
 
 static int inter_decide(misa_b200_ctx *c, int n_runaway) {
+    if (c->opt_inter_dev) return idev_decide(c);
     InterHost *h = IH(c);
     const Geo &g = c->geo;
     h->ghost.clear(); // inter_atom_list->clearGhost(), reference src/atom.cpp:22
@@ -499,6 +529,7 @@ static void periodic_shift(const misa_b200_ctx *c, int dim, int dir, double off[
 
 // InterAtomList::exchangeInter (reference src/atom/inter_atom_list.cpp:19-25, src/pack/inter_particle_packer.cpp:59-121)
 static int inter_exchange(misa_b200_ctx *c) {
+    if (c->opt_inter_dev) return idev_exchange(c);
     InterHost *h = IH(c);
     static const unsigned flags[3][2] = {{OUT_XL, OUT_XB}, {OUT_YL, OUT_YB}, {OUT_ZL, OUT_ZB}};
     for (int dim = 0; dim < 3; dim++) {
@@ -537,6 +568,7 @@ static int inter_exchange(misa_b200_ctx *c) {
 
 // InterAtomList::borderInter (reference src/atom/inter_atom_list.cpp:47-53, src/pack/inter_border_packer.cpp:12-106)
 static int inter_border(misa_b200_ctx *c) {
+    if (c->opt_inter_dev) { TRY(idev_border(c)); return idev_publish(c); };
     InterHost *h = IH(c);
     const Geo &g = c->geo;
     const int gh[3] = {2 * g.gx, g.gy, g.gz}, bx[3] = {2 * g.nx, g.ny, g.nz}, ex[3] = {2 * g.sxc, g.sy, g.sz};
@@ -584,6 +616,7 @@ static int inter_border(misa_b200_ctx *c) {
 
 // inter part of DfEmbedPacker (reference src/pack/df_embed_packer.cpp:38-43,60-66): df of border inter atoms
 static int inter_halo_df(misa_b200_ctx *c) {
+    if (c->opt_inter_dev) return idev_halo_df(c);
     InterHost *h = IH(c);
     for (int dim = 0; dim < 3; dim++) {
         std::vector<double> send[2], recv[2];
@@ -599,6 +632,26 @@ static int inter_halo_df(misa_b200_ctx *c) {
     return 0;
 }
 
+// the reference offsets decoded into (dx2, dy, dz), once per context
+static int idev_rel(misa_b200_ctx *c) {
+    InterDevBuf *b = g_inter_dev[c];
+    const Geo &g = c->geo;
+    if (b->d_rel) return 0;
+    std::vector<int3> rel(2 * (size_t)c->n_full);
+    const long long sx = 2LL * g.sxc, sy = g.sy;
+    for (int p = 0; p < 2; p++)
+        for (int q = 0; q < c->n_full; q++) {
+            const long long off = c->ref_off[p][q];
+            long long dx = ((off % sx) + sx + sx / 2) % sx - sx / 2;
+            long long r = (off - dx) / sx;
+            long long dy = ((r % sy) + sy + sy / 2) % sy - sy / 2;
+            long long dz = (r - dy) / sy;
+            rel[(size_t)p * c->n_full + q] = make_int3((int)dx, (int)dy, (int)dz);
+        }
+    CU(cudaMalloc((void **)&b->d_rel, rel.size() * sizeof(int3)));
+    CU(cudaMemcpy(b->d_rel, rel.data(), rel.size() * sizeof(int3), cudaMemcpyHostToDevice));
+    return 0;
+}
 // ---- device mirror + pair kernels ---------------------------------------------------------------------
 static int inter_push_mirror(misa_b200_ctx *c, bool with_df) {
     InterHost *h = IH(c);
@@ -607,7 +660,8 @@ static int inter_push_mirror(misa_b200_ctx *c, bool with_df) {
     const int nl = (int)h->local.size(), ng = (int)h->ghost.size(), n = nl + ng;
     if (n == 0) return 0;
     REQ(n <= b->cap, MISA_B200_EOVERFLOW, "inter mirror overflow");
-    if (!b->d_rel) { // decode the reference offsets into (dx2, dy, dz)
+    TRY(idev_rel(c));
+    if (false) { // (decoded by idev_rel)
         std::vector<int3> rel(2 * (size_t)c->n_full);
         const long long sx = 2LL * g.sxc, sy = g.sy;
         for (int p = 0; p < 2; p++)
@@ -664,6 +718,7 @@ static int inter_push_mirror(misa_b200_ctx *c, bool with_df) {
 static int inter_make_index(misa_b200_ctx *c) { return 0; } // buckets are (re)built around each pair kernel
 
 static int inter_run_pairs(misa_b200_ctx *c, bool force) {
+    if (c->opt_inter_dev) return idev_run_pairs(c, force);
     InterHost *h = IH(c);
     InterDevBuf *b = g_inter_dev[c];
     const int nl = (int)h->local.size(), n = nl + (int)h->ghost.size();
@@ -701,6 +756,7 @@ static int inter_rho(misa_b200_ctx *c) { return inter_run_pairs(c, false); }
 static int inter_force(misa_b200_ctx *c) { return inter_run_pairs(c, true); }
 
 static int inter_thermo(misa_b200_ctx *c, double *d_out) {
+    if (c->opt_inter_dev) return idev_thermo(c, d_out);
     InterHost *h = IH(c);
     InterDevBuf *b = g_inter_dev[c];
     const int nl = (int)h->local.size(), n = nl + (int)h->ghost.size();

@@ -488,8 +488,11 @@ k_soa_to_aos(const Geo g, unsigned long long *__restrict__ aos, const Soa s, con
 //      ghost site's ideal position follows from its extended lattice index; images carry the periodic shift).
 //      Sizes the pruned stencil: two lattice atoms can only be within r_c if their SITES are closer than
 //      r_c + 2*dmax (atom::decide bounds dmax by 0.2a, reference src/atom.cpp:42). ---------------------------
+// hist (optional): 256 bins, how many valid atoms carry each displacement level -- the host picks the marking level from it
 __global__ void __launch_bounds__(MISA_BLOCK)
-k_max_displacement(const Geo g, const Soa s, unsigned long long *__restrict__ out) {
+k_max_displacement(const Geo g, const Soa s, unsigned long long *__restrict__ out, unsigned int *__restrict__ hist = nullptr) {
+    __shared__ unsigned int sh[256];
+    if (hist) { sh[threadIdx.x] = 0; __syncthreads(); }
     const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double dist = 0.0;
     if (d < g.n_ext && s.type[d] >= 0) {
@@ -504,8 +507,49 @@ k_max_displacement(const Geo g, const Soa s, unsigned long long *__restrict__ ou
         const double ex = s.x[0][d] - xt, ey = s.x[1][d] - yt, ez = s.x[2][d] - zt;
         dist = ex * ex + ey * ey + ez * ez;
     }
-    if (d < g.n_ext) s.ulev[d] = disp_level(dist, g.a);
+    if (d < g.n_ext) {
+        const unsigned char lev = disp_level(dist, g.a);
+        s.ulev[d] = lev;
+        if (hist && s.type[d] >= 0) atomicAdd(&sh[lev], 1u);
+    }
     report_max(dist, out);
+    if (hist) {
+        __syncthreads();
+        if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+    }
+}
+// ---- partner bound of the stencil pruning as a FIELD (serial path: run-aways / inter atoms around, every site's level just
+//      re-measured by k_max_displacement, ghosts included): pmax[cell] = the largest displacement level of any valid atom within
+//      the stencil reach (+-g cells) of the cell -- a separable running maximum, three passes over the 1.2 M cells. A warp then
+//      bounds its partners by the maximum of pmax over its own 32 cells: exact locality, no threshold -- a cascade core keeps
+//      its long lists, the thermal rest of the box its short prefixes (with one global bound a single re-occupied site 0.3 a off
+//      its position made every warp of the box loop all 228 offsets). ----------------------------------------------------------
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_pmax_x(const Geo g, const int8_t *__restrict__ type, const unsigned char *__restrict__ ulev, unsigned char *__restrict__ out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.H) return;
+    const int cx = (int)(c % g.sxc);
+    const long long row = c - cx;
+    int m = 0;
+    for (int x = max(0, cx - g.gx); x <= min(g.sxc - 1, cx + g.gx); x++) {
+        const long long d = row + x;
+        if (type[d] >= 0) m = max(m, (int)ulev[d]);
+        if (type[d + g.H] >= 0) m = max(m, (int)ulev[d + g.H]);
+    }
+    out[c] = (unsigned char)m;
+}
+// running maximum along y (axis 1) or z (axis 2) with radius r
+__global__ void __launch_bounds__(MISA_BLOCK)
+k_pmax_axis(const Geo g, const int axis, const int r, const unsigned char *__restrict__ in, unsigned char *__restrict__ out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.H) return;
+    const long long q = c / g.sxc;
+    const int y = (int)(q % g.sy), z = (int)(q / g.sy);
+    const int n = axis == 1 ? g.sy : g.sz, p = axis == 1 ? y : z;
+    const long long stride = axis == 1 ? g.sxc : (long long)g.sxc * g.sy;
+    int m = 0;
+    for (int k = max(0, p - r); k <= min(n - 1, p + r); k++) m = max(m, (int)in[c + (long long)(k - p) * stride]);
+    out[c] = (unsigned char)m;
 }
 
 // ---- diagnostics: sum m v^2 (configuration::mvv, reference src/system_configuration.cpp:61-84), E_pot ---

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "nccl_dl.cuh"
 #include "inter.cuh"
+#include "inter_dev.cuh"
 #include "eam_smem.cuh"
 #include "eam_fast.cuh"
 #include "eam_sym.cuh"
@@ -394,7 +395,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
     cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
-    cudaFree(c->d_census); cudaFreeHost(c->h_census);
+    cudaFree(c->d_census); cudaFreeHost(c->h_census); cudaFree(c->d_pmax); cudaFree(c->d_ptmp);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
     cudaFree(c->d_ghost_dst); cudaFree(c->d_ghost_src); cudaFree(c->d_ghost_shift);
@@ -848,6 +849,7 @@ extern "C" int misa_b200_upload_atoms(misa_b200_ctx *c, const void *atoms) {
     TRY(census_fetch(c));
     c->have_atoms = true;
     c->dmax_valid = false;
+    c->pmax_valid = false;
     return 0;
 }
 extern "C" int misa_b200_download_atoms(misa_b200_ctx *c, void *atoms) {
@@ -906,6 +908,10 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "p2p_fence")) c->opt_p2p_fence = value;
     else if (!strcmp(name, "push_fused")) c->opt_push_fused = value;
     else if (!strcmp(name, "host_slabs")) c->opt_host_slabs = value;
+    else if (!strcmp(name, "inter_dev")) {
+        REQ(c->n_inter_local + c->n_inter_ghost == 0, MISA_B200_ESTATE, "inter_dev: switch before any inter atom exists");
+        c->opt_inter_dev = value;
+    }
     else if (!strcmp(name, "slab_planes")) { c->slab_T = std::max(3, value); c->n_slabs = 0; }
     else if (!strcmp(name, "p2p_debug")) {
         if (value && !c->d_p2p_dbg) {
@@ -1081,12 +1087,23 @@ static void pick_list(const misa_b200_ctx *c, const int *&offs, int &n_off, int 
     if (n_near) *n_near = c->level_near[L];
 }
 
-// measure dmax over the whole ghost-extended array (positions as they are now, ghosts included)
+// measure dmax over the whole ghost-extended array (positions as they are now, ghosts included) and, for the stencil pruning
+// of the serial path, the per-cell partner bound (kernels.cuh:k_pmax_*)
 static int measure_displacement(misa_b200_ctx *c) {
+    const Geo &g = c->geo;
     c->mark_valid = false;   // levels are re-measured for every site, nothing is marked
+    c->pmax_valid = false;
     CU(cudaMemsetAsync(c->d_stepinfo + 1, 0, sizeof(unsigned long long), c->stream));
-    k_max_displacement<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo, c->s, c->d_stepinfo + 1);
+    k_max_displacement<<<nblk(g.n_ext), MISA_BLOCK, 0, c->stream>>>(g, c->s, c->d_stepinfo + 1);
     c->launches++;
+    if (c->opt_prune && c->opt_mark) {
+        if (!c->d_pmax) { TRY(dmalloc(&c->d_pmax, (size_t)g.H)); TRY(dmalloc(&c->d_ptmp, (size_t)g.H)); }
+        k_pmax_x<<<nblk(g.H), MISA_BLOCK, 0, c->stream>>>(g, c->s.type, c->s.ulev, c->d_pmax);
+        k_pmax_axis<<<nblk(g.H), MISA_BLOCK, 0, c->stream>>>(g, 1, g.gy, c->d_pmax, c->d_ptmp);
+        k_pmax_axis<<<nblk(g.H), MISA_BLOCK, 0, c->stream>>>(g, 2, g.gz, c->d_ptmp, c->d_pmax);
+        c->launches += 3;
+        c->pmax_valid = true;
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_stepinfo + 1, c->d_stepinfo + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1263,6 +1280,7 @@ static LevelSel make_levelsel(const misa_b200_ctx *c, const unsigned long long *
     for (int L = 0; L < misa_b200_ctx::kPairLevels; L++) ls.prefix[L] = c->prefix_n[L];
     ls.H = c->geo.H;
     if (c->mark_valid && c->opt_mark) { ls.hot = c->d_hot; ls.edge = c->d_hot_init; ls.hot_T = c->mark_T_used; ls.hot_epoch = c->mark_epoch; ls.hot_count = c->d_stepinfo + 2; }
+    if (c->pmax_valid && c->opt_mark && !dmax2) ls.pmax = c->d_pmax;   // the host-level (serial) path: positions unchanged since measure_displacement
     if (!c->opt_prune) return ls;
     if (!dmax2) {   // the host's knowledge (serial path): same rounding as pick_list
         if (c->dmax_valid) ls.host_level = (int)std::min(ceil((sqrt(c->dmax2) + 1e-6) / ls.step), 1000.0);
@@ -1717,6 +1735,7 @@ static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false, bool push = fal
     vp.push = push ? c->d_p2p_dev : nullptr;   // band sites store their new position straight into the neighbours' ghosts
     Slot sl(c, MISA_B200_K_VERLET1);
     c->mark_valid = false;
+    c->pmax_valid = false;
     if (c->opt_mark && c->opt_prune) {   // this step's marks carry a fresh epoch byte (1..255): nothing to clear
         c->mark_epoch = c->mark_epoch % 255 + 1;
         c->mark_T_used = c->mark_T_next;
@@ -2072,6 +2091,7 @@ static int step_host_slabs(misa_b200_ctx *c, void *atoms, bool &redo) {
     // the step's words, marks: as verlet1_enqueue
     VerletPar vp = verlet_par(c);
     c->mark_valid = false;
+    c->pmax_valid = false;
     if (c->opt_mark && c->opt_prune) {
         c->mark_epoch = c->mark_epoch % 255 + 1;
         c->mark_T_used = c->mark_T_next;
@@ -2398,6 +2418,7 @@ extern "C" int misa_b200_build_world(misa_b200_ctx *c, uint32_t seed, double t_s
     TRY(census_fetch(c));
     c->have_atoms = true;
     c->dmax_valid = false;
+    c->pmax_valid = false;
     c->minor_valid = false;
     return 0;
 }
@@ -2420,6 +2441,7 @@ static int global_mvv(misa_b200_ctx *c, double sums[2]) {
     cudaFree(d_part);
     CU(e);
     double mvv = c->h_reduce[0], n = c->h_reduce[1];
+    if (c->opt_inter_dev) TRY(idev_sync_host(c));
     for (const HostAtom &a : IH(c)->local) {   // inter list after the lattice, list order (system_configuration.cpp:73-82)
         mvv += (a.v[0] * a.v[0] + a.v[1] * a.v[1] + a.v[2] * a.v[2]) * kMass[a.type];
         n += 1.0;
@@ -2483,6 +2505,7 @@ extern "C" int misa_b200_dump_records(misa_b200_ctx *c, const int32_t begin[3], 
         r = {2 * g.gx, g.gy, g.gz, 2 * g.nx, g.ny, g.nz, 0};
     }
     r.n = (long long)r.nx * r.ny * r.nz;
+    if (c->opt_inter_dev) TRY(idev_sync_host(c));
     const size_t n_inter = IH(c)->local.size();
     const int n_tiles = (int)((r.n + DUMP_TILE - 1) / DUMP_TILE);
     if (!c->d_dump_total) {

@@ -45,6 +45,13 @@ for s in range(chunk, steps + 1, chunk):
     rows.append(dict(step=s, e=e, de_per_atom=(e - e0) / ctx.n_owned, inter=th["n_inter"], runaways_last=th["runaways"], ms_per_step=1e3 * dt / chunk))
     print("step %5d  E %.3f  dE %.3e eV/atom  inter atoms %d  run-aways(last step) %d  %.3f ms/step" % (
         s, e, (e - e0) / ctx.n_owned, th["n_inter"], th["runaways"], 1e3 * dt / chunk), flush=True)
+if os.environ.get("PKA_PROFILE"):          # per-slot CUDA-event times of the last state (inter atoms present)
+    ctx.profile_enable(True)
+    ctx.step(50)
+    pr = ctx.profile_read()
+    ctx.profile_enable(False)
+    print("slots (ms per launch x launches per step):", {k: (round(v[0] / max(v[1], 1), 4), v[1] / 50) for k, v in pr.items() if v[1]}, flush=True)
+    print("stencil stats:", ctx.stencil_stats(), "novac", ctx.query("novac"), "mark level", ctx.query("mark_level"), "dmax", ctx.query("dmax"), flush=True)
 rec = ctx.dump_records(steps)
 vac = ctx.n_owned - (rec.size - rows[-1]["inter"])
 print(json.dumps(dict(cells=n, atoms=ctx.n_owned, pka_ev=energy, dt_ps=1e-4, steps=steps, ms_per_step=1e3 * t_all / steps,
