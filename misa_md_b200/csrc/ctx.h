@@ -45,6 +45,10 @@ struct Soa {
     unsigned long long *id;
     unsigned char *ulev;   // ceil(|x - site| / 0.01a) of the valid atom on the site (k_verlet1 / k_max_displacement): per-warp stencil pruning
     unsigned char *hot;    // [H] per CELL: an atom displaced by more than the marking level sits within reach, or a ghost may (k_verlet1)
+    // Vacant sites are INVISIBLE to the stencil kernels: x holds MISA_VACANT_X (no pair is ever in range, no per-neighbour species
+    // load is needed) and the position the departed atom left behind -- which the reference keeps in the record and reads in
+    // atom::decide (ws::isOutBox(*near_atom), src/atom.cpp:69) -- lives here. Null: feature off (option "vac_sentinel" 0).
+    double *sx[3];
 };
 
 struct InterSoa {  // off-lattice atoms: [0, n_local) local, [cap/2, cap/2 + n_ghost) ghost copies
@@ -100,6 +104,8 @@ struct misa_b200_ctx {
     bool mark_valid = false;
     unsigned char *d_pmax = nullptr, *d_ptmp = nullptr;   // per-cell partner bound of the serial path (kernels.cuh:k_pmax_*)
     bool pmax_valid = false;
+    int *d_low_list = nullptr, *d_low_count = nullptr;   // atoms with a pair below the staged table range, cascade form (eam_fast.cuh:k_low_fix)
+    int opt_low_list = 1;
     int level_n[kLevels] = {0};
     int level_near[kLevels] = {0};        // leading entries (lists are sorted by site distance) that are almost surely in range
     int near_full = 0;
@@ -126,6 +132,7 @@ struct misa_b200_ctx {
     cudaTextureObject_t tex_all = 0;      // int2 view of the whole block: one handle for all four fields (eam_fast.cuh)
     cudaTextureObject_t tex_herm = 0;     // int4 view of d_herm (EAM_PHI_TEX experiment only)
     int opt_tex = 1, opt_novac = 1;
+    int opt_vac_sentinel = 1;             // see Soa::sx
     int opt_fast = 1;                     // third-generation kernels (eam_fast.cuh)
     long long n_valid_sites = -1;         // valid sites at the last census, scaled so that "== geo.n_ext" means none vacant
     bool seen_offlattice = false;         // a run-away / inter atom was reported by any sub-box since the last census

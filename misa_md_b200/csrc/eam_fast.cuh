@@ -263,6 +263,59 @@ __device__ __forceinline__ double generic_force_pair(const double2 *__restrict__
     return -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
 }
 
+// ---- atoms with a pair below the staged range, cascade form (LOWLIST variants + k_low_fix) ----------------------------------
+// A thermal box never has one; there the in-kernel recomputation above (one lane loops, its warp waits) is free. A cascade core
+// has thousands, packed into a few hundred warp units: with one lane looping 100+ offsets of dependent global loads per unit the
+// stencil kernels of a 5 keV cascade ran 1.35x longer than on a thermal box with the same pair count. The LOWLIST variants --
+// launched by the serial (off-lattice) path only -- just append such atoms to a list and store nothing for them; k_low_fix then
+// recomputes each listed atom with a whole warp (lanes stride the FULL offset list, fixed-shape butterfly: deterministic).
+__device__ __forceinline__ void low_append(const LateWait &lw, const int d) {
+    const int k = atomicAdd(lw.low_count, 1);
+    if (k < lw.low_cap) lw.low_list[k] = d;
+}
+template <bool FORCE>
+__global__ void __launch_bounds__(256)
+k_low_fix(const Geo g, const Soa s, const DevTables tb, const double2 *__restrict__ herm, const int8_t *__restrict__ type, const int single,
+          const int *__restrict__ offs, const int n_list, const int *__restrict__ list, const int *__restrict__ count, const int cap, const bool accum,
+          const bool fuse_df) {
+    const int lane = threadIdx.x & 31, n = min(*count, cap);
+    const size_t tstride = (size_t)tb.n_r + 1;
+    const double rc2 = g.rc2, inv_dr = tb.inv_dr;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += (gridDim.x * blockDim.x) >> 5) {
+        const int d = list[w], ti = max((int)s.type[d], 0);
+        const int *off = offs + (d >= g.H ? n_list : 0);
+        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = FORCE ? s.df[d] : 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int q = lane; q < n_list; q += 32) {
+            const int j = d + off[q];
+            const int tj = type ? (int)type[j] : single;
+            const double dx = xi - s.x[0][j], dy = yi - s.x[1][j], dz = zi - s.x[2][j];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (tj >= 0 && d2 < rc2) {
+                if (!FORCE) a0 += generic_rho_pair(herm, tstride, tj, d2, inv_dr, tb.n_r - 1);
+                else {
+                    const double fp = generic_force_pair(herm, tstride, tb.n_types, ti, tj, d2, dfi, s.df[j], inv_dr, tb.n_r - 1);
+                    a0 = fma(dx, fp, a0); a1 = fma(dy, fp, a1); a2 = fma(dz, fp, a2);
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            if (FORCE) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+        }
+        if (lane == 0) {
+            if (!FORCE) {
+                if (accum) a0 += s.rho[d];
+                s.rho[d] = a0;
+                if (fuse_df) s.df[d] = d_embed(tb, ti, a0);
+            } else {
+                if (accum) { a0 += s.f[0][d]; a1 += s.f[1][d]; a2 += s.f[2][d]; }
+                s.f[0][d] = a0; s.f[1][d] = a1; s.f[2][d] = a2;
+            }
+        }
+    }
+}
+
 // ---- K1 rho (+ K2 df fused): atom::latRho / latDf (reference src/atom.cpp:151-192,286-309), full-list gather ----
 // SINGLE: every valid site has type sp.single; staged slot 0 = elec[single], slot 1 = phi[single][single].
 // NOVAC : the census found no vacant site (ghosts included) -> no per-neighbour type test.
@@ -270,7 +323,7 @@ __device__ __forceinline__ double generic_force_pair(const double2 *__restrict__
 // The offset list is sorted by site separation; its first n_near entries (sites >= 0.1a inside the cutoff) are
 // evaluated without any branch (two independent pairs in flight per thread), the rest behind a warp vote.
 // DILUTE: SINGLE loop over the majority tables + the minority-neighbour epilogue (see above).
-template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM, bool DILUTE = false>
+template <bool SINGLE, bool NOVAC, bool FUSE_DF, bool ACCUM, bool DILUTE = false, bool LOWLIST = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
         const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList(), const LateWait lw = LateWait()) {
@@ -374,7 +427,10 @@ EAM_UNROLL(2)
                 }
             }
         }
-        if (__any_sync(0xffffffffu, low)) {
+        low = low && ti >= 0;   // (a vacant central site stores zeros whatever its lanes computed)
+        if (LOWLIST) {          // cascades: such atoms are listed and recomputed by k_low_fix, one warp each (see there)
+            if (low && live) { low_append(lw, d); continue; }
+        } else if (__any_sync(0xffffffffu, low)) {
             if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d);
         }
         if (!live) continue;
@@ -401,7 +457,7 @@ EAM_UNROLL(2)
 // eam::toForce (oracle/pot.c:pot_to_force): phi = z2/r, phi' = z2'/r - phi/r, fpair = -(phi' + emb)/r with
 // emb = rho'_i(r) df_j + rho'_j(r) df_i; z2' and rho' are slopes per knot times 1/dr, factored out:
 //   fpair = -(1/r) * ( (1/dr) * (z2'_p / r + emb_p) - z2 / r^2 )
-template <bool SINGLE, bool NOVAC, bool ACCUM, bool DILUTE = false>
+template <bool SINGLE, bool NOVAC, bool ACCUM, bool DILUTE = false, bool LOWLIST = false>
 __global__ void __launch_bounds__(EAM_THREADS, 1)
 k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const int n_near_h,
           const TexAll tex, const RegionList rl, const LevelSel ls, const MinorList ml = MinorList(), const LateWait lw = LateWait()) {
@@ -564,7 +620,10 @@ EAM_UNROLL(2)
                 }
             }
         }
-        if (__any_sync(0xffffffffu, low)) {
+        low = low && ti >= 0;
+        if (LOWLIST) {
+            if (low && live) { low_append(lw, d); continue; }
+        } else if (__any_sync(0xffffffffu, low)) {
             if (low) {
                 const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types,
                                                   tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d, tic);

@@ -182,7 +182,8 @@ __host__ __device__ __forceinline__ void unit_split(const RegionList &rl, const 
 // did from inside (k_verlet1's positions, k_rho_f's df): that kernel is complete, its stores are performed. push_df: k_rho_f's
 // epilogue stores the new df of band sites into the neighbours' ghosts (kernels.cuh:push_site).
 struct LateWait { const unsigned long long *flags; unsigned long long epoch; unsigned int mask; unsigned int *err; long long limit; int fold_dmax;
-                  const P2pPeers *post; unsigned long long post_epoch; const unsigned long long *post_dmax; const P2pPeers *push_df; };
+                  const P2pPeers *post; unsigned long long post_epoch; const unsigned long long *post_dmax; const P2pPeers *push_df;
+                  int *low_list, *low_count; int low_cap; };   // LOWLIST variants (eam_fast.cuh:k_low_fix)
 __device__ __forceinline__ void post_arrive(const LateWait &lw) {
     if (!lw.post || blockIdx.x != 0 || threadIdx.x >= 27) return;
     const int k = threadIdx.x;

@@ -83,7 +83,7 @@ __global__ void k_gather_sites(const int n, const int *__restrict__ sites, const
     const int d = sites[i];
     HostAtom a;
     a.id = s.id[d]; a.type = s.type[d]; a._pad = 0;
-    for (int k = 0; k < 3; k++) { a.x[k] = s.x[k][d]; a.v[k] = s.v[k][d]; a.f[k] = s.f[k][d]; }
+    for (int k = 0; k < 3; k++) { a.x[k] = site_x(s, k, d, a.type); a.v[k] = s.v[k][d]; a.f[k] = s.f[k][d]; }
     a.rho = s.rho[d]; a.df = s.df[d];
     out[i] = a;
 }
@@ -93,6 +93,7 @@ __global__ void k_vacate(const int n, const int *__restrict__ sites, const Soa s
     if (i >= n) return;
     const int d = sites[i];
     s.type[d] = -1;
+    site_set_x(s, d, -1, s.x[0][d], s.x[1][d], s.x[2][d]);   // the position stays in the record (Soa::sx), the stencil no longer sees it
     s.v[0][d] = 0.0; s.v[1][d] = 0.0; s.v[2][d] = 0.0;
 }
 // atom::decide part 2: vacancy re-occupied by an inter atom (reference src/atom.cpp:69-76)

@@ -206,6 +206,7 @@ k_idev_append_runaways(const Geo g, const Soa s, const InterSoa a, int *__restri
         for (int k = 0; k < 3; k++) { a.x[k][j] = s.x[k][d]; a.v[k][j] = s.v[k][d]; a.f[k][j] = s.f[k][d]; }
         a.rho[j] = s.rho[d]; a.df[j] = s.df[d]; a.type[j] = s.type[d]; a.id[j] = s.id[d];
         s.type[d] = -1;
+        site_set_x(s, d, -1, s.x[0][d], s.x[1][d], s.x[2][d]);   // the position stays in the record (Soa::sx), the stencil no longer sees it
         s.v[0][d] = 0.0; s.v[1][d] = 0.0; s.v[2][d] = 0.0;
     }
     __syncthreads();
@@ -220,7 +221,7 @@ __global__ void k_idev_claim(const Geo g, const Soa s, const InterSoa a, const i
     const WsGeo w = ws_geo(g);
     const int d = ws_near_site_in_sub_box_d(w, a.x[0][i], a.x[1][i], a.x[2][i]);
     // near_atom != nullptr && near_atom->isInterElement() && ws::isOutBox(*near_atom) == IN_BOX (the vacancy's own stale position)
-    const bool cand = d >= 0 && s.type[d] < 0 && ws_is_out_box_d(w, s.x[0][d], s.x[1][d], s.x[2][d]) == 0;
+    const bool cand = d >= 0 && s.type[d] < 0 && ws_is_out_box_d(w, site_x(s, 0, d, -1), site_x(s, 1, d, -1), site_x(s, 2, d, -1)) == 0;
     a.site[i] = cand ? d : -1;
     if (cand) atomicMin(&claim[d], (unsigned)i);
 }

@@ -4,7 +4,25 @@
 #include "ctx.h"
 
 #define MISA_BLOCK 256
+// Position stored for a vacant site (ctx.h Soa::sx): far outside every box (boxes span < 1e4 A) and every cutoff, yet close enough
+// that the spline index of such a "pair" (r / dr ~ 1e8) still fits an int -- the branch-free near loop evaluates out-of-range
+// lanes along, and an index that overflowed read as "row below the staged range" (the exact, slow recompute of the whole atom:
+// measured 1.35x on the stencil kernels of a cascade with 1e30 here)
+#define MISA_VACANT_X 1.0e5
+// the record's position: for a vacant site the stale one the departed atom left behind
+__device__ __forceinline__ double site_x(const Soa &s, const int k, const int d, const int type) { return (type < 0 && s.sx[0]) ? s.sx[k][d] : s.x[k][d]; }
+__device__ __forceinline__ void site_set_x(const Soa &s, const int d, const int type, const double x, const double y, const double z) {
+    if (type < 0 && s.sx[0]) {
+        s.sx[0][d] = x; s.sx[1][d] = y; s.sx[2][d] = z;
+        s.x[0][d] = MISA_VACANT_X; s.x[1][d] = MISA_VACANT_X; s.x[2][d] = MISA_VACANT_X;
+    } else { s.x[0][d] = x; s.x[1][d] = y; s.x[2][d] = z; }
+}
 
+// leave the "vacant sites are invisible" representation: stale positions back into x (option vac_sentinel 0 / sym 1)
+__global__ void __launch_bounds__(256) k_unsentinel(const long long n, const Soa s) {
+    const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n && s.type[d] < 0) { s.x[0][d] = s.sx[0][d]; s.x[1][d] = s.sx[1][d]; s.x[2][d] = s.sx[2][d]; }
+}
 // ---- index helpers ------------------------------------------------------------------------------
 // owned-cell ordinal c in [0, nx*ny*nz) of sub-lattice p -> device index
 __device__ __forceinline__ int owned_cell_to_dev(const Geo &g, int p, long long c, int &cx, int &y, int &z) {
@@ -186,6 +204,15 @@ struct VerletPar { double dt; double c[MISA_MAX_TYPES]; int mark_T; unsigned cha
                    float inv100_a, lev_slack;      // 100 / a and 2e-4 / a, both rounded up (disp_level_fast)
                    const P2pPeers *push;           // non-null: band sites store their new position into the neighbours' ghosts (push_site)
                    long long c_begin, c_end; };    // owned-cell ordinals [c_begin, c_end) of each sub-lattice this launch covers (a z-slab; default: all)
+// what the integrator kernels touch of the state (a kernel parameter of its own: with the whole Soa -- sixteen pointers -- as the
+// parameter the compiler no longer fitted k_verlet1 into 32 registers and spilled freshly loaded values inside the hot path)
+struct SoaV { double *x[3], *v[3]; const double *f[3]; const int8_t *type; unsigned char *ulev; };
+__host__ __device__ inline SoaV soa_v(const Soa &s) {
+    SoaV q;
+    for (int k = 0; k < 3; k++) { q.x[k] = s.x[k]; q.v[k] = s.v[k]; q.f[k] = s.f[k]; }
+    q.type = s.type; q.ulev = s.ulev;
+    return q;
+}
 // dt / (2 m) of species t WITHOUT indexing the kernel parameter dynamically: `vp.c[t]` made the compiler copy the whole
 // parameter struct to local memory in every thread (9 STL + 1 LDL per atom in the SASS of the round-1 kernels)
 __device__ __forceinline__ double kick_coef(const VerletPar &vp, const int t) { return t == 0 ? vp.c[0] : (t == 1 ? vp.c[1] : vp.c[2]); }
@@ -259,7 +286,7 @@ __device__ __noinline__ void verlet1_rare(const int d, const long long cell, con
 // KICK2: the second half-kick of the step that just finished (NewtonMotion::secondstep, same f) is applied first --
 // inside a multi-step call the two streaming passes over v and f become one (bit-identical: the same two rounded adds)
 template <bool KICK2, bool PUSH>
-__device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const VerletPar &vp, const int p, const long long c,
+__device__ __forceinline__ double verlet1_site(const Geo &g, const SoaV &s, const VerletPar &vp, const int p, const long long c,
                                                int *__restrict__ counters, int *__restrict__ runaway_sites, const int runaway_cap) {
     int cx, y, z;
     const int d = owned_cell_to_dev(g, p, c, cx, y, z);
@@ -306,8 +333,8 @@ __device__ __forceinline__ double verlet1_site(const Geo &g, const Soa &s, const
 // PUSH: band sites also store their new position into the neighbours' ghosts (VerletPar::push) -- a variant of its own so that
 // the single-sub-box kernel keeps its 32 registers
 template <bool KICK2, bool PUSH = false>
-__global__ void __launch_bounds__(MISA_BLOCK, PUSH ? 5 : 8)   // 32 registers: eight resident blocks, the latency of the nine loads needs every warp it can get
-k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
+__global__ void __launch_bounds__(MISA_BLOCK, PUSH ? 5 : 8)   // 32 registers (48 with the push): the latency of the nine loads needs every warp it can get
+k_verlet1(const Geo g, const SoaV s, const VerletPar vp, const int blocks_per_parity, int *__restrict__ counters,
           int *__restrict__ runaway_sites, const int runaway_cap, unsigned long long *__restrict__ stepinfo) {
     const int p = blockIdx.x >= blocks_per_parity;
     const int b = blockIdx.x - p * blocks_per_parity;
@@ -330,7 +357,7 @@ k_verlet1(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_par
 }
 // ---- K5 verlet-2: NewtonMotion::secondstep (reference src/newton_motion.cpp:57-74) -------------------
 __global__ void __launch_bounds__(MISA_BLOCK)
-k_verlet2(const Geo g, const Soa s, const VerletPar vp, const int blocks_per_parity) {
+k_verlet2(const Geo g, const SoaV s, const VerletPar vp, const int blocks_per_parity) {
     const int p = blockIdx.x >= blocks_per_parity;
     const int b = blockIdx.x - p * blocks_per_parity;
     const long long c = vp.c_begin + (long long)b * blockDim.x + threadIdx.x;
@@ -365,10 +392,11 @@ __global__ void __launch_bounds__(MISA_BLOCK) k_pack_x2(const Halo2 h, const Soa
     const int d = hi ? h.send1[i] : h.send0[i];
     const double *sh = hi ? h.sh1 : h.sh0;
     double4 r;
-    r.x = __dadd_rn(s.x[0][d], sh[0]);
-    r.y = __dadd_rn(s.x[1][d], sh[1]);
-    r.z = __dadd_rn(s.x[2][d], sh[2]);
-    r.w = (double)s.type[d];
+    const int t = s.type[d];                       // (a vacant site travels with its stale position, like the reference's record)
+    r.x = __dadd_rn(site_x(s, 0, d, t), sh[0]);
+    r.y = __dadd_rn(site_x(s, 1, d, t), sh[1]);
+    r.z = __dadd_rn(site_x(s, 2, d, t), sh[2]);
+    r.w = (double)t;
     reinterpret_cast<double4 *>(hi ? buf1 : buf0)[i] = r;
 }
 __global__ void __launch_bounds__(MISA_BLOCK) k_unpack_x2(const Halo2 h, const Soa s, const double *__restrict__ buf0, const double *__restrict__ buf1) {
@@ -378,7 +406,7 @@ __global__ void __launch_bounds__(MISA_BLOCK) k_unpack_x2(const Halo2 h, const S
     if (hi) i -= h.n0;
     const int d = hi ? h.recv1[i] : h.recv0[i];
     const double4 r = reinterpret_cast<const double4 *>(hi ? buf1 : buf0)[i];
-    s.x[0][d] = r.x; s.x[1][d] = r.y; s.x[2][d] = r.z;
+    site_set_x(s, d, (int)r.w, r.x, r.y, r.z);
     s.type[d] = (int8_t)(int)r.w;
 }
 __global__ void __launch_bounds__(MISA_BLOCK) k_copy_x2(const Halo2 h, const Soa s) {
@@ -388,10 +416,9 @@ __global__ void __launch_bounds__(MISA_BLOCK) k_copy_x2(const Halo2 h, const Soa
     if (hi) i -= h.n0;
     const int a = hi ? h.send1[i] : h.send0[i], b = hi ? h.recv1[i] : h.recv0[i];
     const double *sh = hi ? h.sh1 : h.sh0;
-    s.x[0][b] = __dadd_rn(s.x[0][a], sh[0]);
-    s.x[1][b] = __dadd_rn(s.x[1][a], sh[1]);
-    s.x[2][b] = __dadd_rn(s.x[2][a], sh[2]);
-    s.type[b] = s.type[a];
+    const int t = s.type[a];
+    site_set_x(s, b, t, __dadd_rn(site_x(s, 0, a, t), sh[0]), __dadd_rn(site_x(s, 1, a, t), sh[1]), __dadd_rn(site_x(s, 2, a, t), sh[2]));
+    s.type[b] = (int8_t)t;
 }
 __global__ void __launch_bounds__(MISA_BLOCK) k_pack_12(const Halo2 h, const double *__restrict__ field, double *__restrict__ buf0, double *__restrict__ buf1) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -420,12 +447,13 @@ k_ghost_fill_x(const int n, const int *__restrict__ dst, const int *__restrict__
     const int a = src[i], b = dst[i];
     const int cd = code[i]; // (sx+1) + 3*(sy+1) + 9*(sz+1), shifts applied in x,y,z stage order
     const int kx = cd % 3 - 1, ky = (cd / 3) % 3 - 1, kz = cd / 9 - 1;
-    double x = s.x[0][a], y = s.x[1][a], z = s.x[2][a];
+    const int t = s.type[a];
+    double x = site_x(s, 0, a, t), y = site_x(s, 1, a, t), z = site_x(s, 2, a, t);
     if (kx) x = __dadd_rn(x, kx > 0 ? lx : -lx);
     if (ky) y = __dadd_rn(y, ky > 0 ? ly : -ly);
     if (kz) z = __dadd_rn(z, kz > 0 ? lz : -lz);
-    s.x[0][b] = x; s.x[1][b] = y; s.x[2][b] = z;
-    s.type[b] = s.type[a];
+    site_set_x(s, b, t, x, y, z);
+    s.type[b] = (int8_t)t;
 }
 __global__ void __launch_bounds__(MISA_BLOCK)
 k_ghost_fill_1(const int n, const int *__restrict__ dst, const int *__restrict__ src, double *__restrict__ field) {
@@ -453,8 +481,15 @@ k_aos_to_soa(const long long n_ext, const long long H, const unsigned long long 
     const long long d = ref_to_dev(idx, H);
     const unsigned long long *w = aos + idx * AOS_WORDS;
     if (fields & F_ID) s.id[d] = w[0];
-    if (fields & F_TYPE) s.type[d] = (int8_t)(int)(unsigned)(w[1] & 0xffffffffull);
-    if (fields & F_X) { s.x[0][d] = __longlong_as_double(w[2]); s.x[1][d] = __longlong_as_double(w[3]); s.x[2][d] = __longlong_as_double(w[4]); }
+    if (fields & (F_TYPE | F_X)) {
+        // the record's position goes where the site's (new) occupancy says: vacant sites keep it aside (Soa::sx)
+        const int t_old = s.type[d], t_new = (fields & F_TYPE) ? (int)(int8_t)(int)(unsigned)(w[1] & 0xffffffffull) : t_old;
+        const double x = (fields & F_X) ? __longlong_as_double(w[2]) : site_x(s, 0, (int)d, t_old);
+        const double y = (fields & F_X) ? __longlong_as_double(w[3]) : site_x(s, 1, (int)d, t_old);
+        const double z = (fields & F_X) ? __longlong_as_double(w[4]) : site_x(s, 2, (int)d, t_old);
+        if (fields & F_TYPE) s.type[d] = (int8_t)t_new;
+        if ((fields & F_X) || (t_old < 0) != (t_new < 0)) site_set_x(s, (int)d, t_new, x, y, z);
+    }
     if (fields & F_V) { s.v[0][d] = __longlong_as_double(w[5]); s.v[1][d] = __longlong_as_double(w[6]); s.v[2][d] = __longlong_as_double(w[7]); }
     if (fields & F_F) { s.f[0][d] = __longlong_as_double(w[8]); s.f[1][d] = __longlong_as_double(w[9]); s.f[2][d] = __longlong_as_double(w[10]); }
     if (fields & F_RHO) s.rho[d] = __longlong_as_double(w[11]);
@@ -477,7 +512,10 @@ k_soa_to_aos(const Geo g, unsigned long long *__restrict__ aos, const Soa s, con
     unsigned long long *w = aos + idx * AOS_WORDS;
     if (fields & F_ID) w[0] = s.id[d];
     if (fields & F_TYPE) w[1] = (w[1] & 0xffffffff00000000ull) | (unsigned long long)(unsigned)(int)s.type[d];
-    if (fields & F_X) { w[2] = __double_as_longlong(s.x[0][d]); w[3] = __double_as_longlong(s.x[1][d]); w[4] = __double_as_longlong(s.x[2][d]); }
+    if (fields & F_X) {
+        const int t = s.type[d];
+        w[2] = __double_as_longlong(site_x(s, 0, (int)d, t)); w[3] = __double_as_longlong(site_x(s, 1, (int)d, t)); w[4] = __double_as_longlong(site_x(s, 2, (int)d, t));
+    }
     if (fields & F_V) { w[5] = __double_as_longlong(s.v[0][d]); w[6] = __double_as_longlong(s.v[1][d]); w[7] = __double_as_longlong(s.v[2][d]); }
     if (fields & F_F) { w[8] = __double_as_longlong(s.f[0][d]); w[9] = __double_as_longlong(s.f[1][d]); w[10] = __double_as_longlong(s.f[2][d]); }
     if (fields & F_RHO) w[11] = __double_as_longlong(s.rho[d]);

@@ -121,6 +121,8 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_rho_f<true, false, true, false, true>)); OPTIN((k_rho_f<true, false, false, false, true>));
     OPTIN((k_force_f<true, true, false, true>)); OPTIN((k_force_f<true, false, false, true>));
     OPTIN(k_force_minor_s);
+    OPTIN((k_rho_f<true, true, false, false, false, true>)); OPTIN((k_rho_f<true, false, false, false, false, true>));
+    OPTIN((k_force_f<true, true, false, false, true>)); OPTIN((k_force_f<true, false, false, false, true>));
     OPTIN((k_rho_a<true, false>)); OPTIN((k_rho_a<false, false>)); OPTIN((k_rho_a<true, true>)); OPTIN((k_rho_a<false, true>));
     OPTIN((k_force_a<true, false>)); OPTIN((k_force_a<false, false>)); OPTIN((k_force_a<true, true>)); OPTIN((k_force_a<false, true>));
 #undef OPTIN
@@ -261,6 +263,8 @@ extern "C" int misa_b200_create(const misa_b200_domain *dom, misa_b200_ctx **out
     for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.v[k], n)); TRY(dmalloc(&c->s.f[k], n)); }
     TRY(dmalloc(&c->s.rho, n)); TRY(dmalloc(&c->s.type, n)); TRY(dmalloc(&c->s.id, n)); TRY(dmalloc(&c->s.ulev, n));
     CU(cudaMemset(c->s.ulev, 0xff, n));
+    for (int k = 0; k < 3; k++) c->s.sx[k] = nullptr;
+    if (c->opt_vac_sentinel) for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.sx[k], n)); CU(cudaMemset(c->s.sx[k], 0, n * 8)); }
     {   // hot-cell map (ctx.h): the template marks every cell whose stencil reaches into the ghost shell (ghost levels are not kept)
         const Geo &g = c->geo;
         std::vector<unsigned char> tmpl((size_t)g.H, 1);
@@ -390,6 +394,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaFree(c->d_xyzd);
     for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
     cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id); cudaFree(c->s.ulev); cudaFree(c->d_hot); cudaFree(c->d_hot_init);
+    for (int k = 0; k < 3; k++) cudaFree(c->s.sx[k]);
     cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g); cudaFree(c->d_stepinfo_n);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
@@ -891,6 +896,17 @@ extern "C" int misa_b200_set_timestep(misa_b200_ctx *c, double dt) {
     return 0;
 }
 
+// vacant sites get their stale positions back into x and the side arrays go (Soa::sx)
+static int drop_sentinel(misa_b200_ctx *c) {
+    if (!c->s.sx[0]) return 0;
+    k_unsentinel<<<nblk(c->geo.n_ext), MISA_BLOCK, 0, c->stream>>>(c->geo.n_ext, c->s);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; k++) { cudaFree(c->s.sx[k]); c->s.sx[k] = nullptr; }
+    c->opt_vac_sentinel = 0;
+    return 0;
+}
 extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int value) {
     REQ(c && name, MISA_B200_EINVAL, "null argument");
     if (!strcmp(name, "prune")) c->opt_prune = value;
@@ -900,7 +916,7 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "novac")) c->opt_novac = value;
     else if (!strcmp(name, "fast")) c->opt_fast = value;
     else if (!strcmp(name, "dilute")) c->opt_dilute = value;
-    else if (!strcmp(name, "sym")) c->opt_sym = value;
+    else if (!strcmp(name, "sym")) { c->opt_sym = value; if (value) TRY(drop_sentinel(c)); }   // the pair-symmetric passes read every site's stored position
     else if (!strcmp(name, "p2p")) c->opt_p2p = value;
     else if (!strcmp(name, "mark")) c->opt_mark = value;
     else if (!strcmp(name, "late")) c->opt_late = value;
@@ -908,6 +924,13 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
     else if (!strcmp(name, "p2p_fence")) c->opt_p2p_fence = value;
     else if (!strcmp(name, "push_fused")) c->opt_push_fused = value;
     else if (!strcmp(name, "host_slabs")) c->opt_host_slabs = value;
+    else if (!strcmp(name, "low_list")) c->opt_low_list = value;
+    else if (!strcmp(name, "vac_sentinel")) {
+        if (!value) TRY(drop_sentinel(c));
+        else REQ(c->s.sx[0] || !c->have_atoms, MISA_B200_ESTATE, "vac_sentinel: switch on before atoms are uploaded");
+        if (value && !c->s.sx[0]) for (int k = 0; k < 3; k++) { TRY(dmalloc(&c->s.sx[k], (size_t)c->geo.n_ext)); CU(cudaMemset(c->s.sx[k], 0, (size_t)c->geo.n_ext * 8)); }
+        c->opt_vac_sentinel = value;
+    }
     else if (!strcmp(name, "inter_dev")) {
         REQ(c->n_inter_local + c->n_inter_ghost == 0, MISA_B200_ESTATE, "inter_dev: switch before any inter atom exists");
         c->opt_inter_dev = value;
@@ -1190,6 +1213,9 @@ static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes)
 static inline bool no_vacancy(const misa_b200_ctx *c) {
     return c->opt_novac && c->n_valid_sites == c->geo.n_ext && !c->seen_offlattice;
 }
+// The stencil kernels may skip the per-neighbour species test: no site is vacant -- or vacant sites are invisible to them
+// (their stored position is MISA_VACANT_X, ctx.h Soa::sx). A single-species question: alloys load the species anyway.
+static inline bool no_type_test(const misa_b200_ctx *c) { return no_vacancy(c) || (c->opt_novac && c->s.sx[0] != nullptr); }
 
 // Dilute alloy (one species holds >= 90 % of the valid sites): the SINGLE-species loop over the majority tables plus
 // the minority-neighbour epilogue (eam_fast.cuh). Needs the static lists of prepare(), nothing off-lattice since, and
@@ -1422,6 +1448,28 @@ static int sym_b_grid(const misa_b200_ctx *c, const RegionList &rl) {
     return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)std::max(c->sm_count, 1) * 16));
 }
 
+// Cascade form of the "pair below the staged range" recomputation (eam_fast.cuh:k_low_fix): serial path with inter atoms around,
+// single species, whole-box launch
+static const int kLowCap = 1 << 20;
+static bool low_list_ok(const misa_b200_ctx *c, const StagePlan &sp, bool accum, bool fuse_df, const StencilOpt &so) {
+    return c->opt_low_list && has_inter(c) && sp.single >= 0 && !accum && !fuse_df && so.region == 0 && so.z0 < 0 && !so.dmax2 && !so.late;
+}
+static int low_list_arm(misa_b200_ctx *c, LateWait &lw, int which) {
+    if (!c->d_low_list) { TRY(dmalloc(&c->d_low_list, (size_t)kLowCap)); TRY(dmalloc(&c->d_low_count, 2)); }
+    CU(cudaMemsetAsync(c->d_low_count + which, 0, sizeof(int), c->stream));
+    lw.low_list = c->d_low_list; lw.low_count = c->d_low_count + which; lw.low_cap = kLowCap;
+    return 0;
+}
+static int low_fix_launch(misa_b200_ctx *c, const StagePlan &sp, bool force, bool with_type, int which) {
+    const int grid = std::max(1, c->sm_count) * 2;
+    if (force) k_low_fix<true><<<grid, 256, 0, c->stream>>>(c->geo, c->s, c->tab, sp.g_elec[0], with_type ? c->s.type : nullptr, sp.single, c->d_off_full, c->n_full,
+                                                           c->d_low_list, c->d_low_count + which, kLowCap, false, false);
+    else k_low_fix<false><<<grid, 256, 0, c->stream>>>(c->geo, c->s, c->tab, sp.g_elec[0], with_type ? c->s.type : nullptr, sp.single, c->d_off_full, c->n_full,
+                                                       c->d_low_list, c->d_low_count + which, kLowCap, false, false);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
 static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilOpt &so = StencilOpt()) {
     const Geo &g = c->geo;
     const int bpp = nblk(g.n_cells_owned);
@@ -1439,7 +1487,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
     if (so.late && !late) TRY(p2p_wait(c, c->stream));   // the push this launch consumes: waited for in front of it
     if (c->opt_fast && c->tex_all && planned_any) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
-        const bool novac = no_vacancy(c), single = sp.single >= 0;
+        const bool novac = no_type_test(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
         const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
@@ -1479,6 +1527,14 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         }
 #define RHO_F(S, N, F, A) k_rho_f<S, N, F, A><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw)
 #define RHO_FA(S, N) do { if (accum) RHO_F(S, N, false, true); else if (fuse_df) RHO_F(S, N, true, false); else RHO_F(S, N, false, false); } while (0)
+        if (low_list_ok(c, sp, accum, fuse_df, so)) {
+            TRY(low_list_arm(c, lw, 0));
+            if (novac) k_rho_f<true, true, false, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw);
+            else k_rho_f<true, false, false, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw);
+            c->launches++;
+            CU(cudaGetLastError());
+            return low_fix_launch(c, sp, false, !novac, 0);
+        }
         if (single && novac) RHO_FA(true, true); else if (single) RHO_FA(true, false); else RHO_FA(false, false);
 #undef RHO_FA
 #undef RHO_F
@@ -1623,7 +1679,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     // second generation's staged/divergent one (1.50 vs 1.18 ms at 97:2:1), so multi-species force stays on k_force_s
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
-        const bool novac = no_vacancy(c), single = sp.single >= 0;
+        const bool novac = no_type_test(c), single = sp.single >= 0;
 #if EAM_PHI_TEX
         const int phi_row0 = single ? (c->tab.n_types + sp.single * c->tab.n_types + sp.single) * (c->tab.n_r + 1) : 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride, c->tex_herm, phi_row0};
@@ -1635,6 +1691,14 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         if (rl.units == 0) return 0;
 #define FORCE_F(S, N) do { if (accum) k_force_f<S, N, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList()); \
                            else k_force_f<S, N, false><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw); } while (0)
+        if (low_list_ok(c, sp, accum, false, so)) {
+            TRY(low_list_arm(c, lw, 1));
+            if (novac) k_force_f<true, true, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw);
+            else k_force_f<true, false, false, false, true><<<grid, EAM_THREADS, sb, c->stream>>>(g, c->s, c->tab, sp, c->d_off_full, c->n_full, c->near_full, tex, rl, ls, MinorList(), lw);
+            c->launches++;
+            CU(cudaGetLastError());
+            return low_fix_launch(c, sp, true, !novac, 1);
+        }
         if (single && novac) FORCE_F(true, true); else if (single) FORCE_F(true, false); else FORCE_F(false, false);
 #undef FORCE_F
         c->launches++;
@@ -1743,7 +1807,7 @@ static int verlet1_enqueue(misa_b200_ctx *c, bool kick2 = false, bool push = fal
         c->mark_valid = true;
     }
     CU(cudaMemsetAsync(c->d_stepinfo, 0, 3 * sizeof(unsigned long long) + sizeof(int), c->stream));   // [0..2] + counters[0] (run-aways)
-#define V1(K, P) k_verlet1<K, P><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo)
+#define V1(K, P) k_verlet1<K, P><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, soa_v(c->s), vp, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo)
     if (vp.push) { if (kick2) V1(true, true); else V1(false, true); }
     else { if (kick2) V1(true, false); else V1(false, false); }
 #undef V1
@@ -1790,7 +1854,7 @@ extern "C" int misa_b200_pass_verlet2(misa_b200_ctx *c) {
     const VerletPar vp = verlet_par(c);
     {
         Slot sl(c, MISA_B200_K_VERLET2);
-        k_verlet2<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(c->geo, c->s, vp, bpp);
+        k_verlet2<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(c->geo, soa_v(c->s), vp, bpp);
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -2116,7 +2180,7 @@ static int step_host_slabs(misa_b200_ctx *c, void *atoms, bool &redo) {
         VerletPar v = vp;
         v.c_begin = z0 * cells_plane; v.c_end = z1 * cells_plane;
         const int bpp = nblk(v.c_end - v.c_begin);
-        k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, v, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
+        k_verlet1<false><<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, soa_v(c->s), v, bpp, c->d_counters, c->d_runaway, c->inter_cap, c->d_stepinfo);
         const int m0 = c->slab_map_ofs[k], m = c->slab_map_ofs[k + 1] - m0;
         if (m > 0)
             k_ghost_fill_x<<<nblk(m), MISA_BLOCK, 0, c->stream>>>(m, c->d_slab_dst + m0, c->d_slab_src + m0, c->d_slab_code + m0, c->s, c->dom.meas_global_length[0],
@@ -2140,7 +2204,7 @@ static int step_host_slabs(misa_b200_ctx *c, void *atoms, bool &redo) {
         VerletPar v = vp;
         v.c_begin = z0 * cells_plane; v.c_end = z1 * cells_plane;
         const int bpp = nblk(v.c_end - v.c_begin);
-        k_verlet2<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, c->s, v, bpp);
+        k_verlet2<<<2 * bpp, MISA_BLOCK, 0, c->stream>>>(g, soa_v(c->s), v, bpp);
         const long long i0 = (long long)(g.gz + z0) * plane_recs, i1 = (long long)(g.gz + z1) * plane_recs;
         k_soa_to_aos<<<nblk(i1 - i0), MISA_BLOCK, 0, c->stream>>>(g, (unsigned long long *)c->d_aos_out, c->s, F_ALL, 1, i0, i1);
         c->launches += 2;
