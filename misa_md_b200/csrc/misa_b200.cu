@@ -2388,14 +2388,14 @@ extern "C" int misa_b200_eam_rho_calc(misa_b200_ctx *c, void *atoms, double cuto
     TRY(census_fetch(c));
     TRY(measure_displacement(c));
     TRY(launch_rho(c, false, true));
-    return d2h_aos(c, atoms, F_RHO, 1);
+    return d2h_aos(c, atoms, F_RHO, 2);   // only the owned box crosses PCIe on the way back: ghost records are not ours to write
 }
 extern "C" int misa_b200_eam_df_calc(misa_b200_ctx *c, void *atoms, double cutoff_radius) {
     TRY(hook_common(c, atoms, cutoff_radius));
-    TRY(h2d_aos(c, atoms, F_TYPE | F_RHO));
+    TRY(h2d_aos(c, atoms, F_TYPE | F_RHO, c->have_atoms ? 1 : 0));   // latDf reads and writes owned sites only (src/atom.cpp:286-309)
     c->have_atoms = true;
     TRY(launch_df(c));
-    return d2h_aos(c, atoms, F_DF, 1);
+    return d2h_aos(c, atoms, F_DF, 2);
 }
 extern "C" int misa_b200_eam_force_calc(misa_b200_ctx *c, void *atoms, double cutoff_radius) {
     TRY(hook_common(c, atoms, cutoff_radius));
@@ -2405,7 +2405,7 @@ extern "C" int misa_b200_eam_force_calc(misa_b200_ctx *c, void *atoms, double cu
     TRY(census_fetch(c));
     TRY(measure_displacement(c));
     TRY(launch_force(c, true));
-    return d2h_aos(c, atoms, F_F, 1);
+    return d2h_aos(c, atoms, F_F, 2);
 }
 
 // -------------------------------------------------------------------------------------------------
