@@ -155,7 +155,10 @@ int misa_b200_download_inter(misa_b200_ctx *ctx, void *inter_atoms, size_t cap, 
 int misa_b200_set_timestep(misa_b200_ctx *ctx, double dt);              /* NewtonMotion::setTimestepLength */
 int misa_b200_prepare(misa_b200_ctx *ctx);   /* exchangeAtomFirst + clearForce + computeEam (simulation.cpp:137-145) */
 int misa_b200_step(misa_b200_ctx *ctx, int n_steps); /* firststep .. secondstep, n times */
-/* the same loop body on a HOST AoS array: upload, n steps on the device, download (array coherent on return) */
+/* the same loop body on a HOST AoS array: upload, n steps on the device, download. On return the OWNED lattice records are
+ * current (ghost records are neither read nor written after the first call). Atoms that ran away are not in the array: they
+ * live in the library's inter-atom list (misa_b200_download_inter / misa_b200_dump_records) and their sites come back vacant.
+ * The host must not change the occupancy (type) of records between calls -- use misa_b200_upload_atoms for that. */
 int misa_b200_step_host(misa_b200_ctx *ctx, void *atoms, int n_steps);
 int misa_b200_setv(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy); /* atom::setv */
 int misa_b200_collision_step(misa_b200_ctx *ctx, const int32_t lat[4], const double direction[3], double energy);
@@ -212,11 +215,18 @@ int misa_b200_pass_verlet2(misa_b200_ctx *ctx); /* NewtonMotion::secondstep */
  *   "pipe" 1   step without a host round trip on its critical path; "overlap" -1, "reserve" 8: interior / boundary split
  *              of the stencil launches around a staged NCCL exchange
  *   "p2p" -1   ghost exchange by direct stores into the neighbours' HBM when all of them are peer-mapped (0: NCCL);
- *   "late" 1   wait for the neighbours' push inside the stencil kernels (interior units first) */
+ *   "late" 1   wait for the neighbours' push inside the stencil kernels (interior units first)
+ *   "push_fused" 1  sync-free step: k_verlet1 / k_rho_f store band sites' positions / df into the neighbours' ghosts themselves
+ *              (0: push kernels); "dmax_flags" 1: displacement maxima travel on the push flags (0: all-reduce in front of rho);
+ *              "p2p_fence" 2: ARRIVE from a follow-up kernel (push kernels only); "p2p_timeout_s" 30; "p2p_debug" 0
+ *   "inter_dev" 1   off-lattice atoms resident on the device (csrc/inter_dev.cuh; 0: the host-list form, before any exists)
+ *   "vac_sentinel" 1  vacant sites invisible to the stencil kernels (their record's position kept aside); "low_list" 1
+ *   "host_slabs" 1 / "slab_planes" 3   misa_b200_step_host on one sub-box as a pipeline of z-slabs */
 int misa_b200_set_option(misa_b200_ctx *ctx, const char *name, int value);
 
 /* read-only introspection (tests, benches): "n_off", "n_full", "n_half", "dmax", "single", "novac", "dilute", "n_minor", "sym",
- * "smem_bytes", "pipe_steps", "pipe_redo", "mark_level", "mark_count", "p2p", "p2p_error" */
+ * "smem_bytes", "pipe_steps", "pipe_redo", "host_slab_steps", "host_slab_redo", "mark_level", "mark_count", "p2p", "p2p_error",
+ * "p2p_dbg_<x|df>_<head|body|tail|all>" */
 int misa_b200_query(misa_b200_ctx *ctx, const char *name, double *value);
 
 /* ---- multi-GPU: one sub-box per GPU (replaces libcomm's comm::neiSendReceive over MPI; call sites atom.cpp:114,131,145,
