@@ -39,6 +39,10 @@ struct StagePlan {
     int rows_s;                         // staged rows per table (row_lo .. n_r)
     int off_bytes;                      // byte offset of the table area inside dynamic smem (after the offsets)
     int single;                         // >= 0: every valid site has this type (single-species fast path)
+    // src[k] != null: staged slot k is copied from there instead (rows of 16 bytes like the Hermite tables). Used by the
+    // monomial form of the single-species rho kernel: slot 0 = (c3, c4), slot 1 = (c5, c6) of the reference's own
+    // 7-coefficient rows of elec[maj] (eam_fast.cuh, EAM_MONO_RHO)
+    const double2 *src[EAM_MAX_STAGED];
 };
 
 // ---- TMA / mbarrier plumbing (1-D bulk copies; SASS: UBLKCP) -----------------------------------------
@@ -78,7 +82,7 @@ __device__ __forceinline__ double2 *stage_tables(const StagePlan &sp, unsigned c
         mbar_expect_tx(mbar, bytes * (uint32_t)sp.n_staged);
         for (int k = 0; k < sp.n_staged; k++) {
             const int id = sp.staged_id[k];
-            const double2 *src = (id < MISA_MAX_TYPES ? sp.g_elec[id] : sp.g_phi[id - MISA_MAX_TYPES]) + sp.row_lo;
+            const double2 *src = (sp.src[k] ? sp.src[k] : (id < MISA_MAX_TYPES ? sp.g_elec[id] : sp.g_phi[id - MISA_MAX_TYPES])) + sp.row_lo;
             unsigned char *dst = reinterpret_cast<unsigned char *>(s_tab + (size_t)k * sp.rows_s);
             for (uint32_t o = 0; o < bytes; o += 32768u)
                 tma_load_1d(dst + o, reinterpret_cast<const unsigned char *>(src) + o, min(32768u, bytes - o), mbar);

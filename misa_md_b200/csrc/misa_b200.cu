@@ -399,7 +399,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g); cudaFree(c->d_stepinfo_n);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
-    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm);
+    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm); cudaFree(c->d_c34); cudaFree(c->d_c56);
     cudaFree(c->d_census); cudaFreeHost(c->h_census); cudaFree(c->d_pmax); cudaFree(c->d_ptmp);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
@@ -748,6 +748,22 @@ static int build_hermite(misa_b200_ctx *c, const misa_b200_table *elec, const mi
     c->d_herm = nullptr;
     TRY(dmalloc(&c->d_herm, h.size() / 2));
     CU(cudaMemcpy(c->d_herm, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {   // the value cubic of every r table in the reference's own monomial form, as two half rows (eam_fast.cuh, EAM_MONO_RHO)
+        std::vector<double> a((size_t)ntab * (n + 1) * 2, 0.0), b(a.size(), 0.0);
+        for (int t = 0; t < ntab; t++) {
+            const double *sp = (t < nt ? elec[t] : phi[t - nt]).spline;
+            for (int m = 0; m <= n; m++) {
+                const size_t o = ((size_t)t * (n + 1) + m) * 2;
+                a[o] = sp[(size_t)m * 7 + 3]; a[o + 1] = sp[(size_t)m * 7 + 4];
+                b[o] = sp[(size_t)m * 7 + 5]; b[o + 1] = sp[(size_t)m * 7 + 6];
+            }
+        }
+        cudaFree(c->d_c34); cudaFree(c->d_c56);
+        c->d_c34 = c->d_c56 = nullptr;
+        TRY(dmalloc(&c->d_c34, a.size() / 2)); TRY(dmalloc(&c->d_c56, b.size() / 2));
+        CU(cudaMemcpy(c->d_c34, a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_c56, b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     c->hermite_ok = ok;
 #if EAM_PHI_TEX
     {
@@ -1489,6 +1505,13 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_type_test(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
+#if EAM_MONO_RHO
+        if (single || dilute_ok(c, sp, accum)) {   // every SINGLE-template variant below: the reference's monomial rows of elec[maj] in both slots
+            const int maj = sp.staged_id[0];
+            sp.src[0] = c->d_c34 + (size_t)maj * (c->tab.n_r + 1);
+            sp.src[1] = c->d_c56 + (size_t)maj * (c->tab.n_r + 1);
+        }
+#endif
         const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
