@@ -522,6 +522,13 @@ def fp64_view(kernels, stats, atoms):
             inst = FP64_INST[k]["eval"] * stats["evals_per_atom"] + FP64_INST[k]["test"] * (stats["offsets_per_atom"] - stats["evals_per_atom"])
             rate = inst * atoms / (kernels[k]["ms"] * 1e-3)
             out[k] = {"fp64_inst_per_atom": inst, "achieved_lanes_per_s": rate, "achieved_tflops_fma_equiv": 2 * rate / 1e12, "frac": rate / pk["dfma_per_s"]}
+            # SURVEY.md section 8d's ALGORITHMIC count (what the reference's loop needs, not what this kernel issues):
+            # K1 = N_off x 8 + N_pair x (sqrt + 7 FMA), K3 = N_pair x (sqrt + div + 3 x (index + 8 FMA) + 9); FMA = 2 flop
+            n_off, n_pair = stats["offsets_per_atom"], stats["pairs_per_atom"]
+            alg = n_off * 8 + n_pair * (1 + 14) if k == "rho" else n_pair * (1 + 1 + 3 * (1 + 16) + 9)
+            out[k]["algorithmic_flop_per_atom"] = alg
+            out[k]["algorithmic_tflops"] = alg * atoms / (kernels[k]["ms"] * 1e-3) / 1e12
+            out[k]["algorithmic_frac"] = out[k]["algorithmic_tflops"] / pk["fp64_tflops"]
     return out
 
 
