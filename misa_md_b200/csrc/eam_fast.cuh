@@ -231,6 +231,19 @@ __device__ __forceinline__ double tex_f64(const cudaTextureObject_t t, const int
     const int2 v = tex1Dfetch<int2>(t, i);
     return __hiloint2double(v.y, v.x);
 }
+// EAM_NB_LDG (measurement only, default 0): bit k set = field k of the NEIGHBOUR (0 x, 1 y, 2 z, 3 df) is read with
+// ld.global.nc on the LSU pipe instead of a texture fetch. Measured in round 2 (profiles/r04a_*): every field moved costs
+// 2.6 LSU wavefronts per warp-level pair and +0.03 ... +0.05 ms per kernel -- the LSU data pipe (78 % busy in rho, 83 % in force,
+// saturating at ~89 %) is the wall of these kernels, the texture front end is half idle (4 cycles per warp-wide TLD, 50 % / 38 %
+// busy). DESIGN.md section 4.3d.
+#ifndef EAM_NB_LDG
+#define EAM_NB_LDG 0
+#endif
+template <int K>
+__device__ __forceinline__ double nb_f64(const cudaTextureObject_t t, const int ns, const double *__restrict__ field, const int j) {
+    if ((EAM_NB_LDG >> K) & 1) return __ldg(field + j);
+    return tex_f64(t, j + K * ns);
+}
 
 // ---- dilute alloys (one species >= 90 % of the sites, e.g. Fe-Cu-Ni 97:2:1) ------------------------------------
 // The per-lane staged-or-global choice of the multi-species variants makes nearly every warp-level pair issue BOTH
@@ -405,7 +418,7 @@ EAM_UNROLL(EAM_UNROLL_NEAR)
             const int j = d + off[q];
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
-            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+            const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             pair(d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj);
         }
@@ -414,7 +427,7 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const int j = d + off[q];
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
-            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+            const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
             if (__any_sync(0xffffffffu, in)) pair(d2, in, tj);
@@ -529,7 +542,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         int mmin = 0x7fffffff;  // smallest row index of any evaluated pair (out-of-range lanes have large ones)
         auto pair = [&](const double dx, const double dy, const double dz, const double d2, const bool in, const int tj, const int j) {
             const double recip = rsqrt_fast(d2);
-            const double dfj = tex_f64(tx, j + 3 * ns);
+            const double dfj = nb_f64<3>(tx, ns, s.df, j);
             const Split sx = split_fast(d2 * recip, inv_dr, n_m1, row_lo);
             mmin = min(mmin, (NEEDTYPE && !in) ? 0x7fffffff : sx.m0);
             const HBasis hb = hbasis(sx.p);
@@ -587,7 +600,7 @@ EAM_UNROLL(EAM_UNROLL_NEAR)
             const int j = d + off[q];
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
-            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+            const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             pair(dx, dy, dz, d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj, j);
         }
@@ -596,7 +609,7 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const int j = d + off[q];
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
-            const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
+            const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
             if (__any_sync(0xffffffffu, in)) pair(dx, dy, dz, d2, in, tj, j);
