@@ -508,6 +508,45 @@ def timed_config(env, cells, ratio, args, clocks=None):
     return ctx, res
 
 
+def pka_config(env, cells, args):
+    """BASELINE.json configs[3]: PKA collision cascade in bcc Fe (reference stage machine of example/config.yaml:58-65 --
+    thermalise at dt 1 fs, rescale to 300 K, setv on one atom, cascade at dt 0.1 fs; frontend/md_simulation.cpp:40-80), all in
+    resident mode. Timed: the last `steps` of the cascade, when off-lattice atoms and vacancies are around (serial path, inter
+    kernels, low-list recompute). One sub-box only."""
+    from misa_md_b200 import synth
+    ctx = env.context((cells,) * 3)
+    ctx.build_world(seed=466953, t_set=600.0, ratio=(1, 0, 0))
+    ctx.set_timestep(DT)
+    ctx.prepare()
+    ctx.step(args.equil)
+    ctx.rescale_to(300.0)
+    ctx.step(50)
+
+    def energy():
+        th = ctx.thermo()
+        return 0.5 * th["mvv"] * synth.MVV2E + th["pe"], th
+    ctx.set_timestep(1e-4)
+    ctx.collision_step((cells // 2, cells // 2, cells // 2, 0), (1.0, 3.0, 5.0), args.pka_ev)
+    e0, _ = energy()
+    lead = args.pka_steps
+    ctx.step(lead)                                   # the cascade develops (untimed)
+    _, th0 = energy()
+    ms = ctx.timed_steps(args.steps)
+    e1, th1 = energy()
+    ctx.profile_enable(True)
+    ctx.step(min(args.steps, 50))
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    atoms = ctx.n_owned
+    res = {"workload": "PKA cascade %.0f eV in bcc Fe %d^3 cells (%d atoms), dt 0.1 fs, steps %d..%d after the kick" % (args.pka_ev, cells, atoms, lead, lead + args.steps),
+           "value": atoms * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps, "steps": args.steps, "atoms_total": atoms,
+           "inter_atoms": [int(th0["n_inter"]), int(th1["n_inter"])], "runaways_last_step": int(th1["runaways"]),
+           "energy_drift_ev_per_atom": (e1 - e0) / atoms, "pipelined_steps": int(ctx.query("pipe_steps")),
+           "slots_ms_x_per_step": {k: [v[0] / max(v[1], 1), v[1] / min(args.steps, 50)] for k, v in prof.items() if v[1]}}
+    ctx.close()
+    return res
+
+
 def fp64_view(kernels, stats, atoms):
     """The two stencil kernels against the fp64 pipe: fp64 warp-instruction lanes per second over the measured DFMA lane rate."""
     p = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
@@ -567,8 +606,10 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "bytes_per_atom": BYTES_PER_ATOM[dom], "atoms_per_launch": atoms_per_gpu,
-                "note": "rho/force are bound by the shared-memory gather rate and the fp64 pipe, not by HBM (DESIGN.md section 4): "
-                        "see roofline_fp64; whole-step HBM fraction in step_hbm_frac; ncu_pipes = committed capture, % of peak",
+                "note": "rho/force are bound by the LSU data pipe (32 lanes gathering random 16-byte table rows from shared memory), not by "
+                        "HBM: ncu_pipes.lsu_wavefronts_pct against a measured saturation of 89 % of that pipe (DESIGN.md section 4.3d, "
+                        "profiles/r04a_*); fp64 view in roofline_fp64; whole-step HBM fraction in step_hbm_frac; ncu_pipes = committed capture, % of peak",
+                "lsu_wall": {"saturation_pct": 89.0, "source": "profiles/r04a_tex_frontend_ldg_all.csv (all neighbour fields on the LSU pipe)"},
                 "ncu_pipes": ncu_pipes}
 
     # ---- e2e: host AoS buffers through the C ABI, H2D + D2H inside the timed region --------------------
@@ -626,6 +667,9 @@ def run_b200(args):
         c3, r3 = timed_config(env, 200, args.ratio, args)
         c3.close()
         configs["cells200"] = r3
+    if "pka" in extra and n_gpus == 1:
+        # configs[3]: PKA collision cascade (inter-atom and run-away paths under load)
+        configs["pka_cascade"] = pka_config(env, cells, args)
 
     line = {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -660,7 +704,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity self-check against the CPU oracle")
     ap.add_argument("--no-hooks", action="store_true", help="skip the reference-driver-on-hooks leg (N=1)")
-    ap.add_argument("--configs", default="alloy,cells200", help="extra BASELINE configs timed after the headline one")
+    ap.add_argument("--configs", default="alloy,cells200,pka", help="extra BASELINE configs timed after the headline one")
+    ap.add_argument("--pka-ev", type=float, default=5000.0, help="PKA energy of the cascade config (eV)")
+    ap.add_argument("--pka-steps", type=int, default=900, help="untimed cascade steps between the kick and the timed region")
     args = ap.parse_args()
     if args.gpus not in GRIDS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")

@@ -112,6 +112,37 @@ __device__ __forceinline__ void rows_ldg(const double2 *__restrict__ tab, const 
     a = __ldg(tab + m);
     b = __ldg(tab + m + 1);
 }
+// ---- pairs that do NOT come from the staged tables (minority species of an alloy, rows below the staged range): the interval's
+// cubic in the reference's own monomial form, fetched with ONE 256-bit load (LDG.E.ENL2.256, sm_100) of a 32-byte aligned row.
+// The Hermite block needs rows m and m + 1 -- two 128-bit loads that straddle a 32-byte sector every other time; for a scattered
+// gather (every lane its own row) the cost is the number of sector requests, which this halves, and value + slope come out of
+// five fused multiply-adds (Horner + synthetic division) instead of the 16 of the basis form.
+struct Row4 { double c3, c4, c5, c6; };
+__device__ __forceinline__ Row4 mono_row(const double *__restrict__ mono, const size_t row) {
+    Row4 r;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.c3), "=d"(r.c4), "=d"(r.c5), "=d"(r.c6) : "l"(mono + 4 * row));
+    return r;
+}
+__device__ __forceinline__ double mono_val(const Row4 &r, const double p) { return fma(fma(fma(r.c3, p, r.c4), p, r.c5), p, r.c6); }
+__device__ __forceinline__ double mono_der(const Row4 &r, const double p) {      // d/dp = (3 c3 p + 2 c4) p + c5
+    const double b2 = fma(r.c3, p, r.c4);
+    return fma(fma(r.c3, p, b2), p, fma(b2, p, r.c5));
+}
+__device__ __forceinline__ void mono_val_der(const Row4 &r, const double p, double &v, double &d) {
+    const double b2 = fma(r.c3, p, r.c4), b1 = fma(b2, p, r.c5);
+    v = fma(b1, p, r.c6);
+    d = fma(fma(r.c3, p, b2), p, b1);
+}
+// one pair force from the monomial block: phi[ti][tj] value + slope, elec[ti] / elec[tj] slopes (per knot; 1/dr factored out)
+__device__ __forceinline__ double mono_fpair(const double *__restrict__ mono, const size_t tstride, const int nt, const int ti, const int tj, const int m,
+                                             const double p, const double recip, const double dfi, const double dfj, const double inv_dr) {
+    double z2, z2p;
+    mono_val_der(mono_row(mono, (size_t)(nt + ti * nt + tj) * tstride + m), p, z2, z2p);
+    const double di = mono_der(mono_row(mono, (size_t)ti * tstride + m), p);
+    const double dj = tj == ti ? di : mono_der(mono_row(mono, (size_t)tj * tstride + m), p);
+    const double emb = fma(di, dfj, dj * dfi);
+    return -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
+}
 // EAM_MONO_RHO: the single-species rho kernel evaluates the reference's OWN cubic ((c3 p + c4) p + c5) p + c6 (libpot row columns
 // 3-6) from two staged 16-byte half rows instead of rebuilding it from Hermite data: 3 fp64 instructions instead of 11 per pair
 // (30 -> 22 in the near loop), the same two LDS.128, the same shared-memory footprint (the rho kernel never needed the staged
@@ -160,7 +191,7 @@ __device__ __forceinline__ void build_directory(unsigned long long *dir, const S
 // would move it (and every access in the hot loop) to local memory.
 __device__ __noinline__ double slow_rho_atom(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
                                              const int8_t *__restrict__ type, const int single,
-                                             const double2 *__restrict__ herm, const int n_r, const double inv_dr, const double rc2,
+                                             const double *__restrict__ mono, const int n_r, const double inv_dr, const double rc2,
                                              const int *__restrict__ off, const int n_off, const int d) {
     const double xi = X[d], yi = Y[d], zi = Z[d];
     const size_t tstride = (size_t)n_r + 1;
@@ -173,16 +204,15 @@ __device__ __noinline__ double slow_rho_atom(const double *__restrict__ X, const
         if (tj >= 0 && d2 < rc2) {
             const double r = d2 * rsqrt_fast(d2);
             const Split sx = split_fast(r, inv_dr, n_r - 1, 1);
-            const double2 *row = herm + (size_t)tj * tstride + sx.m;
-            acc += hval(hbasis(sx.p), __ldg(row), __ldg(row + 1));
+            acc += mono_val(mono_row(mono, (size_t)tj * tstride + sx.m), sx.p);
         }
     }
     return acc;
 }
-// herm: the global Hermite block, elec[t] at t * (n_r + 1), phi[ti][tj] at (nt + ti * nt + tj) * (n_r + 1)
+// mono: the global monomial block, elec[t] at t * (n_r + 1), phi[ti][tj] at (nt + ti * nt + tj) * (n_r + 1) (rows of 4 doubles)
 __device__ __noinline__ double3 slow_force_atom(const double *__restrict__ X, const double *__restrict__ Y, const double *__restrict__ Z,
                                                 const double *__restrict__ DF, const int8_t *__restrict__ type, const int single,
-                                                const double2 *__restrict__ herm, const int nt, const int n_r, const double inv_dr,
+                                                const double *__restrict__ mono, const int nt, const int n_r, const double inv_dr,
                                                 const double rc2, const int *__restrict__ off, const int n_off, const int d, const int ti) {
     const double xi = X[d], yi = Y[d], zi = Z[d], dfi = DF[d];
     const size_t tstride = (size_t)n_r + 1;
@@ -195,15 +225,7 @@ __device__ __noinline__ double3 slow_force_atom(const double *__restrict__ X, co
         if (tj >= 0 && d2 < rc2) {
             const double recip = rsqrt_fast(d2);
             const Split sx = split_fast(d2 * recip, inv_dr, n_r - 1, 1);
-            const HBasis hb = hbasis(sx.p);
-            const HSlope hs = hslope(sx.p);
-            const double2 *rp = herm + (size_t)(nt + ti * nt + tj) * tstride + sx.m;
-            const double2 *ri = herm + (size_t)ti * tstride + sx.m;
-            const double2 *rj = herm + (size_t)tj * tstride + sx.m;
-            const double2 p0 = __ldg(rp), p1 = __ldg(rp + 1);
-            const double z2 = hval(hb, p0, p1), z2p = hder(hs, p0, p1);
-            const double emb = hder(hs, __ldg(ri), __ldg(ri + 1)) * DF[j] + hder(hs, __ldg(rj), __ldg(rj + 1)) * dfi;
-            const double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
+            const double fp = mono_fpair(mono, tstride, nt, ti, tj, sx.m, sx.p, recip, dfi, DF[j], inv_dr);
             fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
         }
     }
@@ -267,16 +289,22 @@ struct MinorList {
 };
 // the two species that are not `maj`, in ascending order: which = 0 / 1
 __host__ __device__ __forceinline__ int minor_species(const int maj, const int which) { return which ? (maj == 2 ? 1 : 2) : (maj == 0 ? 1 : 0); }
-// one pair from the GLOBAL Hermite block (any species), same arithmetic as the loops below
-__device__ __forceinline__ double generic_rho_pair(const double2 *__restrict__ herm, const size_t tstride, const int tj, const double d2,
+// one pair from the GLOBAL monomial block (any species)
+__device__ __forceinline__ double generic_rho_pair(const double *__restrict__ mono, const size_t tstride, const int tj, const double d2,
                                                    const double inv_dr, const int n_m1) {
     const double r = d2 * rsqrt_fast(d2);
     const Split sx = split_fast(r, inv_dr, n_m1, 1);
-    const double2 *row = herm + (size_t)tj * tstride + sx.m;
-    return hval(hbasis(sx.p), __ldg(row), __ldg(row + 1));
+    return mono_val(mono_row(mono, (size_t)tj * tstride + sx.m), sx.p);
 }
-__device__ __forceinline__ double generic_force_pair(const double2 *__restrict__ herm, const size_t tstride, const int nt, const int ti, const int tj,
+__device__ __forceinline__ double generic_force_pair(const double *__restrict__ mono, const size_t tstride, const int nt, const int ti, const int tj,
                                                      const double d2, const double dfi, const double dfj, const double inv_dr, const int n_m1) {
+    const double recip = rsqrt_fast(d2);
+    const Split sx = split_fast(d2 * recip, inv_dr, n_m1, 1);
+    return mono_fpair(mono, tstride, nt, ti, tj, sx.m, sx.p, recip, dfi, dfj, inv_dr);
+}
+// the same pair from the global HERMITE block (eam_sym.cuh only: the rejected pair-symmetric passes keep their own arithmetic)
+__device__ __forceinline__ double generic_force_pair_h(const double2 *__restrict__ herm, const size_t tstride, const int nt, const int ti, const int tj,
+                                                       const double d2, const double dfi, const double dfj, const double inv_dr, const int n_m1) {
     const double recip = rsqrt_fast(d2);
     const Split sx = split_fast(d2 * recip, inv_dr, n_m1, 1);
     const HBasis hb = hbasis(sx.p);
@@ -302,7 +330,7 @@ __device__ __forceinline__ void low_append(const LateWait &lw, const int d) {
 }
 template <bool FORCE>
 __global__ void __launch_bounds__(256)
-k_low_fix(const Geo g, const Soa s, const DevTables tb, const double2 *__restrict__ herm, const int8_t *__restrict__ type, const int single,
+k_low_fix(const Geo g, const Soa s, const DevTables tb, const double *__restrict__ herm, const int8_t *__restrict__ type, const int single,
           const int *__restrict__ offs, const int n_list, const int *__restrict__ list, const int *__restrict__ count, const int cap, const bool accum,
           const bool fuse_df) {
     const int lane = threadIdx.x & 31, n = min(*count, cap);
@@ -442,8 +470,14 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             // back from the staged tables; rows below the staged range make the atom `low` (generic recompute) anyway
 EAM_UNROLL(2)
             for (int k = 0; k < maxn; k++) {
-                if (k < nm && nm != MINOR_OVERFLOW) {
-                    const int e = ml.entry[(size_t)k * ml.n_ext + d];   // species are static while the lists are valid: no type gather
+                // entries ascend in the sorted offset list and this warp looped only its first n_off offsets: an entry beyond that
+                // prefix cannot be in range (the pruning rule) and nothing was evaluated for it -- skip it, and stop when no lane
+                // has an entry left inside the prefix
+                int e = 0;
+                bool act = k < nm && nm != MINOR_OVERFLOW;
+                if (act) { e = ml.entry[(size_t)k * ml.n_ext + d]; act = (e & 127) < n_off; }   // species are static while the lists are valid: no type gather
+                if (!__any_sync(0xffffffffu, act)) break;
+                if (act) {
                     const int j = d + moff[e & 127];
                     const int tj = minor_species(ml.maj, e >> 7);
                     const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
@@ -451,12 +485,10 @@ EAM_UNROLL(2)
                     if (d2 < rc2) {
                         const double r = d2 * rsqrt_fast(d2);
                         const Split sx = split_fast(r, inv_dr, n_m1, row_lo);
-                        const HBasis hb = hbasis(sx.p);
-                        const double2 *row = g_herm + (size_t)tj * tstride + sx.m;
                         double vm;      // the majority term exactly as the loop evaluated it
                         if (MONO) vm = mono_val_s(b_el0, b_el1, sx.m, sx.p);
-                        else { double2 r0, r1; rows_s(b_el0, sx.m, r0, r1); vm = hval(hb, r0, r1); }
-                        acc += hval(hb, __ldg(row), __ldg(row + 1)) - vm;
+                        else { double2 r0, r1; rows_s(b_el0, sx.m, r0, r1); vm = hval(hbasis(sx.p), r0, r1); }
+                        acc += mono_val(mono_row(sp.g_mono, (size_t)tj * tstride + sx.m), sx.p) - vm;
                     }
                 }
             }
@@ -465,7 +497,7 @@ EAM_UNROLL(2)
         if (LOWLIST) {          // cascades: such atoms are listed and recomputed by k_low_fix, one warp each (see there)
             if (low && live) { low_append(lw, d); continue; }
         } else if (__any_sync(0xffffffffu, low)) {
-            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d);
+            if (low) acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_mono, tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d);
         }
         if (!live) continue;
         if (ti < 0) {
@@ -623,8 +655,11 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const int *moff = ml.offs + (par ? ml.n_offs : 0);
 EAM_UNROLL(2)
             for (int k = 0; k < maxn; k++) {
-                if (k < nm && nm != MINOR_OVERFLOW) {
-                    const int e = ml.entry[(size_t)k * ml.n_ext + d];   // species are static while the lists are valid: no type gather
+                int e = 0;                                            // (entries beyond the warp's prefix: see k_rho_f)
+                bool act = k < nm && nm != MINOR_OVERFLOW;
+                if (act) { e = ml.entry[(size_t)k * ml.n_ext + d]; act = (e & 127) < n_off; }
+                if (!__any_sync(0xffffffffu, act)) break;
+                if (act) {
                     const int j = d + moff[e & 127];
                     const int tj = minor_species(ml.maj, e >> 7);
                     const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
@@ -642,12 +677,10 @@ EAM_UNROLL(2)
                         rows_s(b_el0, sx.m, r0, r1);
                         const double rho_p_maj = hder(hs, r0, r1);
                         const double fpm = -recip * fma(inv_dr, fma(z2pm, recip, rho_p_maj * (dfi + dfj)), -(z2m * (recip * recip)));
-                        // the pair as it is: phi[maj][tj], rho'_maj * df_j + rho'_tj * df_i
-                        const double2 *rp = g_herm + (size_t)(nt + ml.maj * nt + tj) * tstride + sx.m;
-                        const double2 *rj = g_herm + (size_t)tj * tstride + sx.m;
-                        const double2 p0 = __ldg(rp), p1 = __ldg(rp + 1);
-                        const double z2 = hval(hb, p0, p1), z2p = hder(hs, p0, p1);
-                        const double emb = fma(rho_p_maj, dfj, hder(hs, __ldg(rj), __ldg(rj + 1)) * dfi);
+                        // the pair as it is: phi[maj][tj], rho'_maj * df_j + rho'_tj * df_i (two 256-bit rows of the monomial block)
+                        double z2, z2p;
+                        mono_val_der(mono_row(sp.g_mono, (size_t)(nt + ml.maj * nt + tj) * tstride + sx.m), sx.p, z2, z2p);
+                        const double emb = fma(rho_p_maj, dfj, mono_der(mono_row(sp.g_mono, (size_t)tj * tstride + sx.m), sx.p) * dfi);
                         const double fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip))) - fpm;
                         fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
                     }
@@ -659,7 +692,7 @@ EAM_UNROLL(2)
             if (low && live) { low_append(lw, d); continue; }
         } else if (__any_sync(0xffffffffu, low)) {
             if (low) {
-                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_elec[0], tb.n_types,
+                const double3 f = slow_force_atom(s.x[0], s.x[1], s.x[2], s.df, (NEEDTYPE || DILUTE) ? s.type : nullptr, sp.single, sp.g_mono, tb.n_types,
                                                   tb.n_r, inv_dr, rc2, offs + (par ? n_list : 0), n_off, d, tic);
                 fx = f.x; fy = f.y; fz = f.z;
             }
@@ -735,7 +768,7 @@ EAM_UNROLL(2)
             const double dx = xi - tex_f64(tex.t, j), dy = yi - tex_f64(tex.t, j + tex.ns), dz = zi - tex_f64(tex.t, j + 2 * tex.ns);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             if (tj >= 0 && d2 < rc2) {
-                const double fp = generic_force_pair(g_herm, tstride, nt, ti, tj, d2, dfi, tex_f64(tex.t, j + 3 * tex.ns), inv_dr, n_m1);
+                const double fp = generic_force_pair(sp.g_mono, tstride, nt, ti, tj, d2, dfi, tex_f64(tex.t, j + 3 * tex.ns), inv_dr, n_m1);
                 fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
             }
         }
@@ -803,7 +836,7 @@ EAM_UNROLL(2)
                     emb = fma(hder(hs, r0, r1), dfi, emb);        // + rho'_{maj}(r) df_i
                     fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
                 } else {
-                    fp = generic_force_pair(g_herm, tstride, nt, ti, tj, d2, dfi, dfj, inv_dr, n_m1);
+                    fp = generic_force_pair(sp.g_mono, tstride, nt, ti, tj, d2, dfi, dfj, inv_dr, n_m1);
                 }
                 fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
             }

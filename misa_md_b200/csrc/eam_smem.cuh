@@ -43,6 +43,10 @@ struct StagePlan {
     // monomial form of the single-species rho kernel: slot 0 = (c3, c4), slot 1 = (c5, c6) of the reference's own
     // 7-coefficient rows of elec[maj] (eam_fast.cuh, EAM_MONO_RHO)
     const double2 *src[EAM_MAX_STAGED];
+    // every r table once more as 32-byte rows (c3, c4, c5, c6) of the reference's own 7-coefficient rows, table order as the
+    // Hermite block (elec[t], then phi[ti * n_types + tj]), 32-byte aligned: ONE 256-bit load per (table, interval) for every
+    // pair that does not come from the staged tables (eam_fast.cuh: mono_row)
+    const double *g_mono;
 };
 
 // ---- TMA / mbarrier plumbing (1-D bulk copies; SASS: UBLKCP) -----------------------------------------

@@ -93,7 +93,7 @@ __device__ __noinline__ double3 slow_force_half(const double *__restrict__ X, co
         const double dx = xi - X[j], dy = yi - Y[j], dz = zi - Z[j];
         const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
         double fp = 0.0;
-        if (vi && vj && d2 < rc2) fp = generic_force_pair(herm, tstride, nt, tab_type, tab_type, d2, dfi, DF[j], inv_dr, n_r - 1);
+        if (vi && vj && d2 < rc2) fp = generic_force_pair_h(herm, tstride, nt, tab_type, tab_type, d2, dfi, DF[j], inv_dr, n_r - 1);
         if (q < n_half) pairs[pair_index(d, q, n_half)] = fp;
         fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
     }
@@ -242,7 +242,7 @@ k_rho_b(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
             const int *offs = offs_h;
             int n_off = n_off_h, n_near = 0;
             select_list(ls, offs, n_off, n_near);
-            acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], s.type, sp.single, sp.g_elec[0], tb.n_r, tb.inv_dr, g.rc2, offs + (par ? n_off : 0), n_off, d);
+            acc = slow_rho_atom(s.x[0], s.x[1], s.x[2], s.type, sp.single, sp.g_mono, tb.n_r, tb.inv_dr, g.rc2, offs + (par ? n_off : 0), n_off, d);
         }
         if (!NOVAC && ti < 0) { s.rho[d] = 0.0; continue; }
         s.rho[d] = acc;
@@ -421,7 +421,7 @@ k_force_b(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
             const int *offs = offs_h;
             int n_off = n_off_h, n_near = 0;
             select_list(ls, offs, n_off, n_near);
-            const double3 f = slow_force_atom(X, Y, Z, s.df, s.type, sp.single, sp.g_elec[0], tb.n_types, tb.n_r, tb.inv_dr, g.rc2,
+            const double3 f = slow_force_atom(X, Y, Z, s.df, s.type, sp.single, sp.g_mono, tb.n_types, tb.n_r, tb.inv_dr, g.rc2,
                                               offs + (par ? n_off : 0), n_off, d, max(ti, 0));
             fx = f.x; fy = f.y; fz = f.z;
         }

@@ -399,7 +399,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g); cudaFree(c->d_stepinfo_n);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
-    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm); cudaFree(c->d_c34); cudaFree(c->d_c56);
+    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm); cudaFree(c->d_c34); cudaFree(c->d_c56); cudaFree(c->d_mono);
     cudaFree(c->d_census); cudaFreeHost(c->h_census); cudaFree(c->d_pmax); cudaFree(c->d_ptmp);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
@@ -758,8 +758,19 @@ static int build_hermite(misa_b200_ctx *c, const misa_b200_table *elec, const mi
                 b[o] = sp[(size_t)m * 7 + 5]; b[o + 1] = sp[(size_t)m * 7 + 6];
             }
         }
-        cudaFree(c->d_c34); cudaFree(c->d_c56);
+        cudaFree(c->d_c34); cudaFree(c->d_c56); cudaFree(c->d_mono);
         c->d_c34 = c->d_c56 = nullptr;
+        c->d_mono = nullptr;
+        {
+            std::vector<double> w((size_t)ntab * (n + 1) * 4, 0.0);
+            for (int t = 0; t < ntab; t++) {
+                const double *sp = (t < nt ? elec[t] : phi[t - nt]).spline;
+                for (int m = 0; m <= n; m++)
+                    for (int k = 0; k < 4; k++) w[((size_t)t * (n + 1) + m) * 4 + k] = sp[(size_t)m * 7 + 3 + k];
+            }
+            TRY(dmalloc(&c->d_mono, w.size()));
+            CU(cudaMemcpy(c->d_mono, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
         TRY(dmalloc(&c->d_c34, a.size() / 2)); TRY(dmalloc(&c->d_c56, b.size() / 2));
         CU(cudaMemcpy(c->d_c34, a.data(), a.size() * sizeof(double), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_c56, b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1212,6 +1223,7 @@ static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes)
     memset(&sp, 0, sizeof sp);
     for (int t = 0; t < nt; t++) sp.g_elec[t] = c->d_herm + (size_t)t * (n + 1);
     for (int t = 0; t < nt * nt; t++) sp.g_phi[t] = c->d_herm + (size_t)(nt + t) * (n + 1);
+    sp.g_mono = c->d_mono;
     sp.single = present <= 1 ? maj : -1;
     sp.row_lo = std::max(1, std::min(n - 2, (int)(c->stage_r_lo * c->tab.inv_dr) - 1));
     sp.rows_s = n + 1 - sp.row_lo;
@@ -1478,9 +1490,9 @@ static int low_list_arm(misa_b200_ctx *c, LateWait &lw, int which) {
 }
 static int low_fix_launch(misa_b200_ctx *c, const StagePlan &sp, bool force, bool with_type, int which) {
     const int grid = std::max(1, c->sm_count) * 2;
-    if (force) k_low_fix<true><<<grid, 256, 0, c->stream>>>(c->geo, c->s, c->tab, sp.g_elec[0], with_type ? c->s.type : nullptr, sp.single, c->d_off_full, c->n_full,
+    if (force) k_low_fix<true><<<grid, 256, 0, c->stream>>>(c->geo, c->s, c->tab, sp.g_mono, with_type ? c->s.type : nullptr, sp.single, c->d_off_full, c->n_full,
                                                            c->d_low_list, c->d_low_count + which, kLowCap, false, false);
-    else k_low_fix<false><<<grid, 256, 0, c->stream>>>(c->geo, c->s, c->tab, sp.g_elec[0], with_type ? c->s.type : nullptr, sp.single, c->d_off_full, c->n_full,
+    else k_low_fix<false><<<grid, 256, 0, c->stream>>>(c->geo, c->s, c->tab, sp.g_mono, with_type ? c->s.type : nullptr, sp.single, c->d_off_full, c->n_full,
                                                        c->d_low_list, c->d_low_count + which, kLowCap, false, false);
     c->launches++;
     CU(cudaGetLastError());
@@ -1506,7 +1518,7 @@ static int launch_rho(misa_b200_ctx *c, bool fuse_df, bool accum, const StencilO
         const bool novac = no_type_test(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
 #if EAM_MONO_RHO
-        if (single || dilute_ok(c, sp, accum)) {   // every SINGLE-template variant below: the reference's monomial rows of elec[maj] in both slots
+        if (!sym_ok(c, sp, accum, so) && (single || dilute_ok(c, sp, accum))) {   // every SINGLE-template variant of k_rho_f below: the reference's monomial rows of elec[maj] in both slots (the pair-symmetric pass A keeps the Hermite rows)
             const int maj = sp.staged_id[0];
             sp.src[0] = c->d_c34 + (size_t)maj * (c->tab.n_r + 1);
             sp.src[1] = c->d_c56 + (size_t)maj * (c->tab.n_r + 1);

@@ -1,5 +1,5 @@
 """Dev-only A/B of builds of the same library (nvcc -D variants under build/variants): thermalised 100^3 box, CUDA-event
-slots of rho / force and the step time. usage: python tools/time_variants.py lib1.so lib2.so ..."""
+slots of rho / force and the step time. usage: [RATIO=97,2,1] python tools/time_variants.py lib1.so lib2.so ..."""
 import os, subprocess, sys
 here = os.path.dirname(os.path.abspath(__file__))
 code = r'''
@@ -8,7 +8,8 @@ sys.path.insert(0, os.path.dirname(%r))
 import misa_md_b200 as mb
 from misa_md_b200 import synth
 P = (100, 100, 100)
-st = synth.create_global_state(P)
+ratio = tuple(int(v) for v in os.environ.get("RATIO", "1,0,0").split(","))
+st = synth.create_global_state(P, ratio=ratio)
 ctx = mb.Context(P)
 ctx.make_offsets()
 ctx.set_potential(*mb.capi.potential_in_type_order(mb.capi.read_setfl(mb.SETFL_PATH)))
