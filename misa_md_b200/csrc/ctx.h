@@ -92,6 +92,7 @@ struct misa_b200_ctx {
     std::vector<int64_t> ref_off[4];      // even, odd, half_even, half_odd in REFERENCE index space
     int n_full = 0;
     int *d_off_full = nullptr;            // [2][n_full]
+    int *d_off_full_addr = nullptr, *d_off_levels_addr = nullptr;   // the same lists, every (level, parity) segment sorted by address
     // pruned stencils by displacement level L: every valid atom within L*0.01a of its site => two lattice atoms
     // can only be within r_c if their SITES are closer than (crf + 0.02 L) a. L = 20 is atom::decide's own bound.
     static const int kLevels = 21;

@@ -743,26 +743,53 @@ __global__ void __launch_bounds__(MISA_BLOCK) k_build_minor_lists(const Geo g, c
 }
 // force on the minority atoms, one warp each: lanes stride the offsets of the atom's parity, fixed-shape butterfly
 // reduction (deterministic per atom; atoms are independent of each other)
-__global__ void __launch_bounds__(256) k_force_minor(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h,
+__global__ void __launch_bounds__(128) k_force_minor(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h,
                                                      const int n_off_h, const LevelSel ls, const int *__restrict__ list, const int n, const TexAll tex) {
-    const int *offs = offs_h;
-    int n_off = n_off_h, n_near = 0;
-    select_list(ls, offs, n_off, n_near);
+    const int *offs = offs_h;             // (address-ordered copy of the host's choice: launch_force_minor)
+    int n_off = n_off_h;
+    select_list_addr(ls, offs, n_off);
     const int lane = threadIdx.x & 31;
     const int nt = tb.n_types, n_m1 = tb.n_r - 1;
     const double2 *__restrict__ g_herm = sp.g_elec[0];
     const size_t tstride = (size_t)tb.n_r + 1;
     const double rc2 = g.rc2, inv_dr = tb.inv_dr;
-    for (int w = (blockIdx.x * 256 + threadIdx.x) >> 5; w < n; w += (gridDim.x * 256) >> 5) {
+    // The kernel is LATENCY-bound (one warp per atom, 3-4 trips of dependent gathers: offset -> neighbour fields -> table rows, at
+    // half occupancy): the lane's offsets of both parities live in registers for the whole kernel (lists of up to 128 offsets: every
+    // pruned level of a dilute box), and the neighbour fields of all four trips are requested before the first pair is evaluated.
+    int o_reg[2][4];
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) o_reg[p][k] = lane + 32 * k < n_off ? offs[p * n_off + lane + 32 * k] : 0;
+    for (int w = (blockIdx.x * 128 + threadIdx.x) >> 5; w < n; w += (gridDim.x * 128) >> 5) {
         const int d = list[w];
         const int ti = s.type[d];
         if (ti < 0) continue;                 // cannot happen while the lists are valid (no run-away since they were built)
-        const int *off = offs + (d >= g.H ? n_off : 0);
+        const bool par = d >= g.H;
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         double fx = 0.0, fy = 0.0, fz = 0.0;
-        // every lane gathers a different neighbour: scattered 8-byte loads, on the TEX pipe (idle here) rather than LSU
-EAM_UNROLL(2)
-        for (int q = lane; q < n_off; q += 32) {
+        // every lane gathers a different neighbour; the list is in address order, so consecutive lanes read runs of neighbouring
+        // sites of one row
+        int jj[4], tt[4];
+        double ex[4], ey[4], ez[4], ed[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            jj[k] = d + (par ? o_reg[1][k] : o_reg[0][k]);       // (a lane beyond the list reads the atom itself: excluded below)
+            tt[k] = s.type[jj[k]];
+            ex[k] = tex_f64(tex.t, jj[k]); ey[k] = tex_f64(tex.t, jj[k] + tex.ns); ez[k] = tex_f64(tex.t, jj[k] + 2 * tex.ns);
+            ed[k] = tex_f64(tex.t, jj[k] + 3 * tex.ns);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double dx = xi - ex[k], dy = yi - ey[k], dz = zi - ez[k];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (lane + 32 * k < n_off && tt[k] >= 0 && d2 < rc2) {
+                const double fp = generic_force_pair(sp.g_mono, tstride, nt, ti, tt[k], d2, dfi, ed[k], inv_dr, n_m1);
+                fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
+            }
+        }
+        const int *off = offs + (par ? n_off : 0);
+        for (int q = lane + 128; q < n_off; q += 32) {          // lists longer than 128 offsets (no pruning): the plain loop
             const int j = d + off[q];
             const int tj = s.type[j];
             const double dx = xi - tex_f64(tex.t, j), dy = yi - tex_f64(tex.t, j + tex.ns), dz = zi - tex_f64(tex.t, j + 2 * tex.ns);

@@ -238,6 +238,8 @@ __device__ __forceinline__ int region_unit_to_dev(const Geo &g, const RegionList
 struct LevelSel {
     const unsigned long long *dmax2_bits;   // null: use the list the host passed (second-generation kernels) / host_level
     const int *levels, *full;               // d_off_levels, d_off_full
+    const int *levels_addr, *full_addr;     // the same lists with every (level, parity) segment in ADDRESS order: kernels whose lanes stride
+                                            // one atom's offsets (k_force_minor) then gather runs of neighbouring sites, not 32 sectors
     int n[EAM_LEVELS], near_[EAM_LEVELS], ofs[EAM_LEVELS];
     int n_full, near_full;
     double step;                            // 0.01 a
@@ -263,6 +265,14 @@ __device__ __forceinline__ void select_list(const LevelSel &ls, const int *&offs
     const int L = (int)ceil(d / ls.step);
     if (L < EAM_LEVELS && ls.n[min(L, EAM_LEVELS - 1)] > 0) { offs = ls.levels + ls.ofs[L]; n_off = ls.n[L]; n_near = ls.near_[L]; }
     else { offs = ls.full; n_off = ls.n_full; n_near = ls.near_full; }
+}
+// the same choice from the address-ordered copies (same lengths; no near group there: the order is by address)
+__device__ __forceinline__ void select_list_addr(const LevelSel &ls, const int *&offs, int &n_off) {
+    if (!ls.dmax2_bits) return;
+    const double d = sqrt(__longlong_as_double((long long)*ls.dmax2_bits)) + 1e-6;
+    const int L = (int)ceil(d / ls.step);
+    if (L < EAM_LEVELS && ls.n[min(L, EAM_LEVELS - 1)] > 0) { offs = ls.levels_addr + ls.ofs[L]; n_off = ls.n[L]; }
+    else { offs = ls.full_addr; n_off = ls.n_full; }
 }
 // global displacement level (the bound on the partner atom of any pair)
 __device__ __forceinline__ int level_of_bits(const LevelSel &ls, const unsigned long long bits) {

@@ -395,7 +395,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     for (int k = 0; k < 3; k++) { cudaFree(c->s.v[k]); cudaFree(c->s.f[k]); }
     cudaFree(c->s.rho); cudaFree(c->s.type); cudaFree(c->s.id); cudaFree(c->s.ulev); cudaFree(c->d_hot); cudaFree(c->d_hot_init);
     for (int k = 0; k < 3; k++) cudaFree(c->s.sx[k]);
-    cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels);
+    cudaFree(c->d_aos); cudaFree(c->d_off_full); cudaFree(c->d_off_levels); cudaFree(c->d_off_full_addr); cudaFree(c->d_off_levels_addr);
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g); cudaFree(c->d_stepinfo_n);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
@@ -588,6 +588,19 @@ static int upload_offsets(misa_b200_ctx *c) {
     TRY(dmalloc(&c->d_off_levels, sp.levels.size()));
     CU(cudaMemcpy(c->d_off_full, sp.full.data(), sp.full.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_off_levels, sp.levels.data(), sp.levels.size() * sizeof(int), cudaMemcpyHostToDevice));
+    {   // address-ordered copies (LevelSel::levels_addr): same segments, each sorted ascending
+        std::vector<int> fa(sp.full), la(sp.levels);
+        for (int p = 0; p < 2; p++) std::sort(fa.begin() + (size_t)p * sp.n_full, fa.begin() + (size_t)(p + 1) * sp.n_full);
+        for (int L = 0; L < misa_b200_ctx::kLevels; L++)
+            for (int p = 0; p < 2; p++)
+                std::sort(la.begin() + sp.level_ofs[L] + (size_t)p * sp.level_n[L], la.begin() + sp.level_ofs[L] + (size_t)(p + 1) * sp.level_n[L]);
+        cudaFree(c->d_off_full_addr); cudaFree(c->d_off_levels_addr);
+        c->d_off_full_addr = c->d_off_levels_addr = nullptr;
+        TRY(dmalloc(&c->d_off_full_addr, fa.size()));
+        TRY(dmalloc(&c->d_off_levels_addr, la.size()));
+        CU(cudaMemcpy(c->d_off_full_addr, fa.data(), fa.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_off_levels_addr, la.data(), la.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     c->have_off = true;
     return MISA_B200_OK;
 }
@@ -1342,6 +1355,7 @@ static LevelSel make_levelsel(const misa_b200_ctx *c, const unsigned long long *
     }
     ls.dmax2_bits = dmax2;
     ls.levels = c->d_off_levels; ls.full = c->d_off_full;
+    ls.levels_addr = c->d_off_levels_addr; ls.full_addr = c->d_off_full_addr;
     for (int L = 0; L < misa_b200_ctx::kLevels; L++) { ls.n[L] = c->level_n[L]; ls.near_[L] = c->level_near[L]; ls.ofs[L] = (int)c->level_ofs[L]; }
     return ls;
 }
@@ -1637,8 +1651,10 @@ static int launch_force_minor(misa_b200_ctx *c, const StagePlan &sp, const int *
         }
         return 0;
     }
-    const int mgrid = std::min((c->n_minor + 7) / 8, std::max(1, c->sm_count) * 8);
-    k_force_minor<<<mgrid, 256, 0, c->stream>>>(g, c->s, c->tab, sp, offs, n_off, ls, c->d_minor, c->n_minor, tex);
+    const int mgrid = std::min((c->n_minor + 3) / 4, std::max(1, c->sm_count) * 20);   // 128 threads, ~94 registers: five CTAs per SM
+    // the host's choice of list, in its address-ordered copy (the kernel re-chooses on the device when the level lives there)
+    const int *offs_a = offs == c->d_off_full ? c->d_off_full_addr : c->d_off_levels_addr + (offs - c->d_off_levels);
+    k_force_minor<<<mgrid, 128, 0, c->stream>>>(g, c->s, c->tab, sp, offs_a, n_off, ls, c->d_minor, c->n_minor, tex);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
