@@ -281,13 +281,19 @@ __device__ __forceinline__ double nb_f64(const cudaTextureObject_t t, const int 
 #define MINOR_OVERFLOW 255
 struct MinorList {
     const unsigned char *count;   // [n_ext] entries of site d, MINOR_OVERFLOW: more than MINOR_CAP (atom recomputed generically)
-    const unsigned char *entry;   // [MINOR_CAP][n_ext] bits 0-6: index into offs (n_offs <= 128); bit 7: which of the two minority species
+    const unsigned char *entry;   // [n_ext][MINOR_CAP] bits 0-6: index into offs (n_offs <= 128); bit 7: which of the two minority species.
+                                  // One 16-byte row per site: the epilogues fetch a site's whole list with ONE load behind the main loop
+                                  // instead of one dependent byte load in front of every trip (the epilogue costs its serial latency)
     const int *offs;              // [2][n_offs] the offset list the indices refer to (widest pruned level)
     int n_offs;
     long long n_ext;
     int maj;
 };
 // the two species that are not `maj`, in ascending order: which = 0 / 1
+__device__ __forceinline__ int entry_byte(const uint4 &e, const int k) {
+    const unsigned w = k < 8 ? (k < 4 ? e.x : e.y) : (k < 12 ? e.z : e.w);
+    return (int)((w >> (8 * (k & 3))) & 255u);
+}
 __host__ __device__ __forceinline__ int minor_species(const int maj, const int which) { return which ? (maj == 2 ? 1 : 2) : (maj == 0 ? 1 : 0); }
 // one pair from the GLOBAL monomial block (any species)
 __device__ __forceinline__ double generic_rho_pair(const double *__restrict__ mono, const size_t tstride, const int tj, const double d2,
@@ -465,8 +471,12 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const int nm = ml.count[d];
             low = low || nm == MINOR_OVERFLOW;
             const int maxn = __reduce_max_sync(0xffffffffu, nm == MINOR_OVERFLOW ? 0 : nm);
-            const int *moff = ml.offs + (par ? ml.n_offs : 0);
-            // neighbour fields through the TEX pipe (the LSU pipe is the loaded one), the majority term that is taken
+            const uint4 e16 = __ldg(reinterpret_cast<const uint4 *>(ml.entry) + d);
+            // What the epilogue costs is its serial latency (entry -> neighbour fields -> table rows -> cubic, trip after trip, while
+            // the warp is missing from the main loops that hide each other's latencies): the site's whole list is one 16-byte load and
+            // the offsets come from the staged copy of the sorted list (ml.offs is a prefix of it). Requesting the neighbour fields of
+            // trip k + 1 before trip k is evaluated was measured and lost (inactive lanes fetch too: force 0.875 -> 0.890 ms).
+            // Neighbour fields through the TEX pipe (the LSU pipe is the loaded one), the majority term that is taken
             // back from the staged tables; rows below the staged range make the atom `low` (generic recompute) anyway
 EAM_UNROLL(2)
             for (int k = 0; k < maxn; k++) {
@@ -475,10 +485,10 @@ EAM_UNROLL(2)
                 // has an entry left inside the prefix
                 int e = 0;
                 bool act = k < nm && nm != MINOR_OVERFLOW;
-                if (act) { e = ml.entry[(size_t)k * ml.n_ext + d]; act = (e & 127) < n_off; }   // species are static while the lists are valid: no type gather
+                if (act) { e = entry_byte(e16, k); act = (e & 127) < n_off; }   // species are static while the lists are valid: no type gather
                 if (!__any_sync(0xffffffffu, act)) break;
                 if (act) {
-                    const int j = d + moff[e & 127];
+                    const int j = d + off[e & 127];
                     const int tj = minor_species(ml.maj, e >> 7);
                     const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
                     const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -652,15 +662,15 @@ EAM_UNROLL(EAM_UNROLL_FAR)
             const int nm = mine ? (int)ml.count[d] : 0;
             low = mine && (low || nm == MINOR_OVERFLOW);
             const int maxn = __reduce_max_sync(0xffffffffu, nm == MINOR_OVERFLOW ? 0 : nm);
-            const int *moff = ml.offs + (par ? ml.n_offs : 0);
+            const uint4 e16 = __ldg(reinterpret_cast<const uint4 *>(ml.entry) + d);   // (one load for the list, staged offsets: see k_rho_f)
 EAM_UNROLL(2)
             for (int k = 0; k < maxn; k++) {
                 int e = 0;                                            // (entries beyond the warp's prefix: see k_rho_f)
                 bool act = k < nm && nm != MINOR_OVERFLOW;
-                if (act) { e = ml.entry[(size_t)k * ml.n_ext + d]; act = (e & 127) < n_off; }
+                if (act) { e = entry_byte(e16, k); act = (e & 127) < n_off; }
                 if (!__any_sync(0xffffffffu, act)) break;
                 if (act) {
-                    const int j = d + moff[e & 127];
+                    const int j = d + off[e & 127];
                     const int tj = minor_species(ml.maj, e >> 7);
                     const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
                     const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -725,7 +735,7 @@ __global__ void __launch_bounds__(MISA_BLOCK) k_build_minor_lists(const Geo g, c
         for (int q = 0; q < n_offs; q++) {
             const int tj = type[d + off[q]];
             if (tj >= 0 && tj != maj) {
-                if (cnt < MINOR_CAP) entry[(size_t)cnt * g.n_ext + d] = (unsigned char)(q | (tj == minor_species(maj, 1) ? 128 : 0));
+                if (cnt < MINOR_CAP) entry[(size_t)d * MINOR_CAP + cnt] = (unsigned char)(q | (tj == minor_species(maj, 1) ? 128 : 0));
                 cnt++;
             }
         }

@@ -184,7 +184,7 @@ EAM_UNROLL(EAM_UNROLL_FAR)
 EAM_UNROLL(2)
             for (int k = 0; k < maxn; k++) {
                 if (k < nm && !redo) {
-                    const int e = ml.entry[(size_t)k * ml.n_ext + d];
+                    const int e = ml.entry[(size_t)d * MINOR_CAP + k];
                     const int j = d + moff[e & 127];
                     const int tj = minor_species(ml.maj, e >> 7);
                     const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
@@ -345,7 +345,7 @@ EAM_UNROLL(EAM_UNROLL_FAR)
 EAM_UNROLL(2)
             for (int k = 0; k < maxn; k++) {
                 if (k < nm && nm != MINOR_OVERFLOW) {
-                    const int e = ml.entry[(size_t)k * ml.n_ext + d];
+                    const int e = ml.entry[(size_t)d * MINOR_CAP + k];
                     const int j = d + moff[e & 127];
                     const int tj = minor_species(ml.maj, e >> 7);
                     const double dx = xi - tex_f64(tx, j), dy = yi - tex_f64(tx, j + ns), dz = zi - tex_f64(tx, j + 2 * ns);
