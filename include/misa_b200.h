@@ -211,7 +211,7 @@ int misa_b200_pass_verlet2(misa_b200_ctx *ctx); /* NewtonMotion::secondstep */
  *   "mark" 1   partner bound of that pruning from the cells marked by far-displaced atoms instead of the global maximum
  *   "fuse" 1   rho + df in one kernel when no inter atoms; "fuse_verlet" 1: second half-kick applied by the next firststep
  *   "smem" 1 / "fast" 1 / "tex" 1 / "novac" 1 / "dilute" 1   kernel generations and their fast paths (csrc/eam_*.cuh)
- *   "sym" 0    pair-symmetric passes (each near pair evaluated once): measured slower; "minor_staged" 0: likewise
+ *   "sym" 0    pair-symmetric passes (each near pair evaluated once): measured slower
  *   "pipe" 1   step without a host round trip on its critical path; "overlap" -1, "reserve" 8: interior / boundary split
  *              of the stencil launches around a staged NCCL exchange
  *   "p2p" -1   ghost exchange by direct stores into the neighbours' HBM when all of them are peer-mapped (0: NCCL);

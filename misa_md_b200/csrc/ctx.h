@@ -133,7 +133,6 @@ struct misa_b200_ctx {
     double *d_xyzd = nullptr;             // ONE allocation behind s.x[0..2] and s.df, field stride xyzd_stride doubles
     long long xyzd_stride = 0;
     cudaTextureObject_t tex_all = 0;      // int2 view of the whole block: one handle for all four fields (eam_fast.cuh)
-    cudaTextureObject_t tex_herm = 0;     // int4 view of d_herm (EAM_PHI_TEX experiment only)
     int opt_tex = 1, opt_novac = 1;
     int opt_vac_sentinel = 1;             // see Soa::sx
     int opt_fast = 1;                     // third-generation kernels (eam_fast.cuh)
@@ -145,8 +144,6 @@ struct misa_b200_ctx {
     unsigned char *d_mcount = nullptr, *d_mentry = nullptr;
     int *d_minor = nullptr, *d_minor_count = nullptr; // device indices of the owned minority-species atoms
     int n_minor = 0, minor_maj = 0;
-    int opt_minor_staged = 0;             // minority atoms: per-species launch with that species' tables in shared memory -- measured SLOWER
-                                          // (force 0.987 vs 0.944 ms at 97:2:1: two launches x 154 KB of staging per CTA, 70 KB of L1 left), off
     bool minor_valid = false;
     int opt_smem = 1;                     // use the shared-memory table kernels when possible
     // pair-symmetric stencil passes (eam_sym.cuh): the leading n_half entries of every offset list are the "upper"

@@ -233,22 +233,9 @@ __device__ __noinline__ double3 slow_force_atom(const double *__restrict__ X, co
 }
 
 // one texture handle for x, y, z and df (one allocation, field stride `ns` doubles; ctx.h d_xyzd)
-// EAM_PHI_TEX (experiment, default 0 -- DESIGN.md section 10.1): the single-species force kernel reads the r*phi rows through the
-// TEXTURE path (16-byte texels of the global Hermite block) instead of shared memory, so that the idle TEX pipe takes half
-// of the 64 B of table rows per pair off the load/store path that bounds the kernel.
-#ifndef EAM_PHI_TEX
-#define EAM_PHI_TEX 0
-#endif
-#if EAM_PHI_TEX
-struct TexAll { cudaTextureObject_t t; int ns; cudaTextureObject_t herm; int phi_row0; };
-__device__ __forceinline__ void rows_tex(const cudaTextureObject_t t, const int row, double2 &a, double2 &b) {
-    const int4 u = tex1Dfetch<int4>(t, row), v = tex1Dfetch<int4>(t, row + 1);
-    a = make_double2(__hiloint2double(u.y, u.x), __hiloint2double(u.w, u.z));
-    b = make_double2(__hiloint2double(v.y, v.x), __hiloint2double(v.w, v.z));
-}
-#else
+// (The r*phi rows of the force kernel through this path -- EAM_PHI_TEX, 16-byte texels of the Hermite block -- were measured twice and
+// removed: 0.638 -> 0.827 ms in round 1, no gain with every neighbour field on the LSU path in round 2)
 struct TexAll { cudaTextureObject_t t; int ns; };
-#endif
 __device__ __forceinline__ double tex_f64(const cudaTextureObject_t t, const int i) {
     const int2 v = tex1Dfetch<int2>(t, i);
     return __hiloint2double(v.y, v.x);
@@ -592,11 +579,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
             double z2, z2p, emb;
             double2 r0, r1;
             if (SINGLE) {
-#if EAM_PHI_TEX
-                rows_tex(tex.herm, tex.phi_row0 + sx.m, r0, r1);
-#else
                 rows_s(b_ph0, sx.m, r0, r1);
-#endif
                 z2 = hval(hb, r0, r1);
                 z2p = hder(hs, r0, r1);
                 rows_s(b_el0, sx.m, r0, r1);
@@ -818,74 +801,8 @@ __global__ void __launch_bounds__(128) k_force_minor(const Geo g, const Soa s, c
     }
 }
 
-// ---- minority atoms with THEIR tables staged: one launch per minority species t, slots 0 = elec[maj], 1 = elec[t],
-//      2 = phi[t][maj] (97 % of a minority atom's pairs are with majority neighbours). k_force_minor gathers six scattered
-//      32-byte sectors per pair from the global block and is LSU-bound on them (profiles/r01s_alloy_kernel_times.csv: 126 us
-//      for 60 k atoms); here those pairs cost three conflicting-at-worst shared-memory row pairs like the main loop's.
-//      MEASURED AND REJECTED (profiles/r01ag_bench_n1_alloy*.json): force 0.987 ms against 0.944 ms with k_force_minor -- two
-//      launches, 154 KB of table staging per CTA and only 70 KB of L1 left for the scattered neighbour fetches. Kept behind
-//      option minor_staged (default 0) with its parity test. ------
-__global__ void __launch_bounds__(EAM_THREADS, 1)
-k_force_minor_s(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const int *__restrict__ offs_h, const int n_off_h, const LevelSel ls,
-                const int *__restrict__ list, const int n, const TexAll tex, const int species) {
-    const int *offs = offs_h;
-    int n_off = n_off_h, n_near = 0;
-    select_list(ls, offs, n_off, n_near);
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint64_t mbar;
-    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_off);
-    const int *s_off = reinterpret_cast<const int *>(smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
-    const uint32_t b_maj = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
-    const uint32_t b_own = b_maj + ((uint32_t)sp.rows_s << 4);
-    const uint32_t b_phi = b_own + ((uint32_t)sp.rows_s << 4);
-    const int nt = tb.n_types, n_m1 = tb.n_r - 1, row_lo = sp.row_lo, maj = sp.staged_id[0];
-    const double2 *__restrict__ g_herm = sp.g_elec[0];
-    const size_t tstride = (size_t)tb.n_r + 1;
-    const double rc2 = g.rc2, inv_dr = tb.inv_dr;
-    for (int w = blockIdx.x * wpc + warp; w < n; w += gridDim.x * wpc) {
-        const int d = list[w];
-        const int ti = s.type[d];
-        if (ti != species) continue;
-        const int *off = s_off + (d >= g.H ? n_off : 0);
-        const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
-        double fx = 0.0, fy = 0.0, fz = 0.0;
-EAM_UNROLL(2)
-        for (int q = lane; q < n_off; q += 32) {
-            const int j = d + off[q];
-            const int tj = s.type[j];
-            const double dx = xi - tex_f64(tex.t, j), dy = yi - tex_f64(tex.t, j + tex.ns), dz = zi - tex_f64(tex.t, j + 2 * tex.ns);
-            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            if (tj >= 0 && d2 < rc2) {
-                const double dfj = tex_f64(tex.t, j + 3 * tex.ns);
-                double fp;
-                const double recip = rsqrt_fast(d2);
-                const Split sx = split_fast(d2 * recip, inv_dr, n_m1, row_lo);
-                if (tj == maj && sx.m0 >= row_lo) {
-                    const HBasis hb = hbasis(sx.p);
-                    const HSlope hs = hslope(sx.p);
-                    double2 r0, r1;
-                    rows_s(b_phi, sx.m, r0, r1);
-                    const double z2 = hval(hb, r0, r1), z2p = hder(hs, r0, r1);
-                    rows_s(b_own, sx.m, r0, r1);
-                    double emb = hder(hs, r0, r1) * dfj;          // rho'_{ti}(r) df_j
-                    rows_s(b_maj, sx.m, r0, r1);
-                    emb = fma(hder(hs, r0, r1), dfi, emb);        // + rho'_{maj}(r) df_i
-                    fp = -recip * fma(inv_dr, fma(z2p, recip, emb), -(z2 * (recip * recip)));
-                } else {
-                    fp = generic_force_pair(sp.g_mono, tstride, nt, ti, tj, d2, dfi, dfj, inv_dr, n_m1);
-                }
-                fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        }
-        if (lane == 0) { s.f[0][d] = fx; s.f[1][d] = fy; s.f[2][d] = fz; }
-    }
-}
+// (A variant with the minority species' own tables staged in shared memory -- one launch per species, 154 KB of staging per CTA --
+// was built, parity-tested, measured slower (force 0.987 against 0.944 ms, profiles/r01ag_*) and removed in round 2.)
 
 // ---- diagnostics for the fp64 view of the roofline (bench.py, not on the step path): what the stencil kernels LOOP on the
 //      current state -- offsets per atom (the per-warp prefix), pair evaluations per atom (branch-free near group + the far

@@ -120,7 +120,6 @@ static int smem_kernels_init(int optin) {
     OPTIN((k_rho_f<true, true, true, false, true>)); OPTIN((k_rho_f<true, true, false, false, true>));
     OPTIN((k_rho_f<true, false, true, false, true>)); OPTIN((k_rho_f<true, false, false, false, true>));
     OPTIN((k_force_f<true, true, false, true>)); OPTIN((k_force_f<true, false, false, true>));
-    OPTIN(k_force_minor_s);
     OPTIN((k_rho_f<true, true, false, false, false, true>)); OPTIN((k_rho_f<true, false, false, false, false, true>));
     OPTIN((k_force_f<true, true, false, false, true>)); OPTIN((k_force_f<true, false, false, false, true>));
     OPTIN((k_rho_a<true, false>)); OPTIN((k_rho_a<false, false>)); OPTIN((k_rho_a<true, true>)); OPTIN((k_rho_a<false, true>));
@@ -789,20 +788,6 @@ static int build_hermite(misa_b200_ctx *c, const misa_b200_table *elec, const mi
         CU(cudaMemcpy(c->d_c56, b.data(), b.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     c->hermite_ok = ok;
-#if EAM_PHI_TEX
-    {
-        if (c->tex_herm) { cudaDestroyTextureObject(c->tex_herm); c->tex_herm = 0; }
-        cudaResourceDesc rd;
-        cudaTextureDesc td;
-        memset(&rd, 0, sizeof rd); memset(&td, 0, sizeof td);
-        rd.resType = cudaResourceTypeLinear;
-        rd.res.linear.devPtr = c->d_herm;
-        rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindSigned);
-        rd.res.linear.sizeInBytes = h.size() * sizeof(double);
-        td.readMode = cudaReadModeElementType;
-        CU(cudaCreateTextureObject(&c->tex_herm, &rd, &td, nullptr));
-    }
-#endif
     return 0;
 }
 
@@ -985,7 +970,6 @@ extern "C" int misa_b200_set_option(misa_b200_ctx *c, const char *name, int valu
         c->opt_p2p_debug = value;
     }
     else if (!strcmp(name, "p2p_timeout_s")) { c->opt_p2p_timeout_s = std::max(1, value); c->p2p.spin_limit = (long long)c->opt_p2p_timeout_s * 2000000000LL; }
-    else if (!strcmp(name, "minor_staged")) c->opt_minor_staged = value;
     else if (!strcmp(name, "fuse_verlet")) c->opt_fuse_verlet = value;
     else if (!strcmp(name, "pipe")) c->opt_pipe = value;
     else if (!strcmp(name, "reserve")) c->opt_reserve = value;
@@ -1631,26 +1615,11 @@ static int launch_df(misa_b200_ctx *c) {
     CU(cudaGetLastError());
     return 0;
 }
-// atoms of the minority species of a dilute alloy: one launch per species with its tables staged (k_force_minor_s), or the
-// global-table kernel when the three tables do not fit
+// atoms of the minority species of a dilute alloy: one warp each, pairs from the global monomial block
 static int launch_force_minor(misa_b200_ctx *c, const StagePlan &sp, const int *offs, int n_off, const LevelSel &ls, const TexAll &tex) {
     if (c->n_minor <= 0) return 0;
     const Geo &g = c->geo;
     const int nt = c->tab.n_types, maj = sp.staged_id[0];
-    const size_t sb3 = (size_t)sp.off_bytes + (size_t)3 * sp.rows_s * 16;
-    if (c->opt_minor_staged && sb3 + 1024 <= (size_t)c->smem_optin) {
-        for (int t = 0; t < nt; t++) {
-            if (t == maj || c->census[t] == 0) continue;
-            StagePlan s3 = sp;
-            s3.n_staged = 3;
-            s3.staged_id[0] = maj; s3.staged_id[1] = t; s3.staged_id[2] = MISA_MAX_TYPES + t * nt + maj;
-            const int grid = std::max(1, std::min(c->sm_count, (c->n_minor + EAM_THREADS / 32 - 1) / (EAM_THREADS / 32)));
-            k_force_minor_s<<<grid, EAM_THREADS, sb3, c->stream>>>(g, c->s, c->tab, s3, offs, n_off, ls, c->d_minor, c->n_minor, tex, t);
-            c->launches++;
-            CU(cudaGetLastError());
-        }
-        return 0;
-    }
     const int mgrid = std::min((c->n_minor + 3) / 4, std::max(1, c->sm_count) * 20);   // 128 threads, ~94 registers: five CTAs per SM
     // the host's choice of list, in its address-ordered copy (the kernel re-chooses on the device when the level lives there)
     const int *offs_a = offs == c->d_off_full ? c->d_off_full_addr : c->d_off_levels_addr + (offs - c->d_off_levels);
@@ -1701,12 +1670,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     }
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
-#if EAM_PHI_TEX
-        const TexAll tex = {c->tex_all, (int)c->xyzd_stride, c->tex_herm,
-                            (c->tab.n_types + sp.staged_id[0] * c->tab.n_types + sp.staged_id[0]) * (c->tab.n_r + 1)};
-#else
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-#endif
         const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         const MinorList ml = minor_list(c);
@@ -1731,12 +1695,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_type_test(c), single = sp.single >= 0;
-#if EAM_PHI_TEX
-        const int phi_row0 = single ? (c->tab.n_types + sp.single * c->tab.n_types + sp.single) * (c->tab.n_r + 1) : 0;
-        const TexAll tex = {c->tex_all, (int)c->xyzd_stride, c->tex_herm, phi_row0};
-#else
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
-#endif
         const RegionList rl = regions_for(c, so, late);
         const LevelSel ls = make_levelsel(c, stencil_dmax(c, so, late));
         if (rl.units == 0) return 0;
