@@ -29,6 +29,9 @@
 #ifndef EAM_UNROLL_FAR
 #define EAM_UNROLL_FAR 4
 #endif
+#ifndef EAM_OFF_V4
+#define EAM_OFF_V4 1   // near group: four staged offsets per 16-byte shared-memory load (0: one 4-byte load per pair)
+#endif
 #define EAM_PRAGMA(x) _Pragma(#x)
 #define EAM_UNROLL(n) EAM_PRAGMA(unroll n)
 
@@ -383,7 +386,8 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
-    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list);
+    const int n_pad = (n_list + 3) & ~3;              // stride between the two sub-lattices' staged lists: four offsets per 16-byte load
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list, n_pad);
     if (!SINGLE && EAM_MULTI_GENERIC) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
@@ -413,7 +417,7 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         const bool live = d0 >= 0;
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);   // tail lanes shadow lane 0 (loads stay in bounds), store nothing
         const int ti = s.type[d];
-        const int *off = s_off + (par ? n_list : 0);
+        const int *off = s_off + (par ? n_pad : 0);
         const int n_off = warp_list_len(ls, lg, hot_ok, d, d - (par ? ls.H : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d];
         double acc = 0.0;
@@ -434,15 +438,23 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
             }
             acc += in ? v : 0.0;
         };
-EAM_UNROLL(EAM_UNROLL_NEAR)
-        for (int q = 0; q < n_near; q++) {
-            const int j = d + off[q];
+        // the uniform offset loads are LSU wavefronts like any other (5 % of the rho kernel's, 3 % of the force kernel's, on the
+        // pipe that bounds both): four offsets per 16-byte load in the branch-free near group
+        auto near_pair = [&](const int o) {
+            const int j = d + o;
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
             const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             pair(d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj);
+        };
+        const int n_near4 = EAM_OFF_V4 ? (n_near & ~3) : 0;
+        for (int q = 0; q < n_near4; q += 4) {
+            const int4 o4 = *reinterpret_cast<const int4 *>(off + q);
+            near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
         }
+EAM_UNROLL(EAM_UNROLL_NEAR)
+        for (int q = n_near4; q < n_near; q++) near_pair(off[q]);
 EAM_UNROLL(EAM_UNROLL_FAR)
         for (int q = n_near; q < n_off; q++) {
             const int j = d + off[q];
@@ -532,7 +544,8 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint64_t mbar;
     __shared__ unsigned long long dir[EAM_DIR];
-    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list);
+    const int n_pad = (n_list + 3) & ~3;              // (see k_rho_f)
+    const double2 *s_tab = stage_tables(sp, smem, &mbar, offs, 2 * n_list, n_pad);
     if (!SINGLE && EAM_MULTI_GENERIC) { build_directory(dir, sp, tb, s_tab); __syncthreads(); }
     const int *s_off = reinterpret_cast<const int *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = EAM_THREADS / 32;
@@ -562,7 +575,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         const int d = live ? d0 : region_unit_to_dev(g, rl, up, par, 0);
         const int ti = s.type[d];
         const int tic = max(ti, 0);
-        const int *off = s_off + (par ? n_list : 0);
+        const int *off = s_off + (par ? n_pad : 0);
         const int n_off = warp_list_len(ls, lg, hot_ok, d, d - (par ? ls.H : 0));
         const double xi = s.x[0][d], yi = s.x[1][d], zi = s.x[2][d], dfi = s.df[d];
         unsigned long long d_eli = 0;
@@ -620,15 +633,21 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
             fp = in ? fp : 0.0;
             fx = fma(dx, fp, fx); fy = fma(dy, fp, fy); fz = fma(dz, fp, fz);
         };
-EAM_UNROLL(EAM_UNROLL_NEAR)
-        for (int q = 0; q < n_near; q++) {
-            const int j = d + off[q];
+        auto near_pair = [&](const int o) {                  // (four offsets per 16-byte load: see k_rho_f)
+            const int j = d + o;
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
             const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             pair(dx, dy, dz, d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj, j);
+        };
+        const int n_near4 = EAM_OFF_V4 ? (n_near & ~3) : 0;
+        for (int q = 0; q < n_near4; q += 4) {
+            const int4 o4 = *reinterpret_cast<const int4 *>(off + q);
+            near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
         }
+EAM_UNROLL(EAM_UNROLL_NEAR)
+        for (int q = n_near4; q < n_near; q++) near_pair(off[q]);
 EAM_UNROLL(EAM_UNROLL_FAR)
         for (int q = n_near; q < n_off; q++) {
             const int j = d + off[q];

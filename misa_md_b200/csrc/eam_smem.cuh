@@ -74,11 +74,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t phase) {
 }
 
 // Stage the planned tables and the neighbour offsets; returns the shared-memory table area.
+// par_stride > 0: the odd sub-lattice's list starts at that (multiple-of-4) index instead of right behind the even one, the gap
+// holds zeros -- so that four consecutive offsets of either list are ONE aligned 16-byte shared-memory load (eam_fast.cuh)
 __device__ __forceinline__ double2 *stage_tables(const StagePlan &sp, unsigned char *smem, uint64_t *mbar, const int *__restrict__ offs,
-                                                 const int n_off2) {
+                                                 const int n_off2, const int par_stride = 0) {
     int *s_off = reinterpret_cast<int *>(smem);
     double2 *s_tab = reinterpret_cast<double2 *>(smem + sp.off_bytes);
     if (threadIdx.x == 0) mbar_init(mbar, 1);
+    if (par_stride > 0) {
+        const int n = n_off2 >> 1;
+        for (int q = threadIdx.x; q < 2 * par_stride; q += blockDim.x) {
+            const int p = q >= par_stride, r = q - (p ? par_stride : 0);
+            s_off[q] = r < n ? offs[p * n + r] : 0;
+        }
+    } else
     for (int q = threadIdx.x; q < n_off2; q += blockDim.x) s_off[q] = offs[q];
     __syncthreads();
     if (threadIdx.x == 0) {

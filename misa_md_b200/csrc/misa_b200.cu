@@ -1224,7 +1224,7 @@ static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes)
     sp.single = present <= 1 ? maj : -1;
     sp.row_lo = std::max(1, std::min(n - 2, (int)(c->stage_r_lo * c->tab.inv_dr) - 1));
     sp.rows_s = n + 1 - sp.row_lo;
-    sp.off_bytes = (int)((2 * (size_t)c->n_full * sizeof(int) + 127) / 128 * 128);
+    sp.off_bytes = (int)((2 * (size_t)((c->n_full + 3) & ~3) * sizeof(int) + 127) / 128 * 128);   // (each parity's list padded to a multiple of four offsets)
     sp.n_staged = 2;
     sp.staged_id[0] = maj;                              // elec[maj]
     sp.staged_id[1] = MISA_MAX_TYPES + maj * nt + maj;  // phi[maj][maj]
