@@ -669,7 +669,10 @@ def run_b200(args):
         configs["cells200"] = r3
     if "pka" in extra and n_gpus == 1:
         # configs[3]: PKA collision cascade (inter-atom and run-away paths under load)
-        configs["pka_cascade"] = pka_config(env, cells, args)
+        try:
+            configs["pka_cascade"] = pka_config(env, cells, args)
+        except Exception as e:   # the cascade is an extra configuration: its failure is reported in the line, it does not take the line away
+            configs["pka_cascade"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     line = {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
