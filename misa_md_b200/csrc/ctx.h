@@ -121,6 +121,8 @@ struct misa_b200_ctx {
     bool have_pot = false, have_off = false, have_atoms = false;
     // Hermite (value, knot slope) copies of the r tables + the shared-memory staging plan (eam_smem.cuh)
     double2 *d_herm = nullptr;            // [n_types + n_types^2][n_r + 1]
+    double2 *d_ea = nullptr;              // [n_types + n_types^2][n_r + 1]: (knot slope s_m, v_{m+1} - v_m) -- with d_es what a slope-only lookup needs
+    double *d_es = nullptr;               // [n_types + n_types^2][n_r + 1] (+ 2 doubles of padding): knot slopes, dense
     double *d_mono = nullptr;             // [n_types + n_types^2][n_r + 1][4]: (c3, c4, c5, c6), one 256-bit load per interval (eam_fast.cuh)
     double2 *d_c34 = nullptr, *d_c56 = nullptr;   // [n_types + n_types^2][n_r + 1]: columns (3,4) and (5,6) of the caller's 7-coefficient rows
     bool hermite_ok = false;              // caller's 7-coefficient rows are Hermite-consistent (checked on the host)

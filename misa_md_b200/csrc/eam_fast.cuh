@@ -29,6 +29,9 @@
 #ifndef EAM_UNROLL_FAR
 #define EAM_UNROLL_FAR 4
 #endif
+#ifndef EAM_ELEC3
+#define EAM_ELEC3 1    // force kernel, single-species loop: slope of elec[maj] from (s_m, dv_m) + s_{m+1} (StagePlan::half_src)
+#endif
 #ifndef EAM_OFF_V4
 #define EAM_OFF_V4 1   // near group: four staged offsets per 16-byte shared-memory load (0: one 4-byte load per pair)
 #endif
@@ -552,6 +555,9 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const long long upp = rl.units;
     const uint32_t b_el0 = smem_u32(s_tab) - ((uint32_t)sp.row_lo << 4);
     const uint32_t b_ph0 = b_el0 + ((uint32_t)sp.rows_s << 4);
+    // dense slopes of elec[maj] behind the 16-byte slots (staged from slope row_lo & ~1): address of slope m = b_es + 8 m
+    constexpr bool e3 = EAM_ELEC3 && SINGLE;              // (the host stages it for exactly these variants: misa_b200.cu:plan_elec3)
+    const uint32_t b_es = smem_u32(s_tab + (size_t)sp.n_staged * sp.rows_s) - ((uint32_t)(sp.row_lo & ~1) << 3);
     const double rc2 = g.rc2, inv_dr = tb.inv_dr;
     const int n_m1 = tb.n_r - 1, row_lo = sp.row_lo, ns = tex.ns;
     const cudaTextureObject_t tx = tex.t;
@@ -559,6 +565,18 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
     const int nt = tb.n_types; (void)nt;
     const double2 *__restrict__ g_herm = sp.g_elec[0];
     const size_t tstride = (size_t)tb.n_r + 1;
+    // slope (per knot) of elec[maj] on interval m: the same three products as hder() -- g11 s_{m+1} + g10 s_m + g01 (v_{m+1} - v_m)
+    auto elec_slope = [&](const HSlope &hs, const int m) -> double {
+        if (e3) {
+            double s0, dv, s1;
+            asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(s0), "=d"(dv) : "r"(b_el0 + ((uint32_t)m << 4)));
+            asm("ld.shared.f64 %0, [%1+8];" : "=d"(s1) : "r"(b_es + ((uint32_t)m << 3)));
+            return fma(hs.g11, s1, fma(hs.g10, s0, hs.g01 * dv));
+        }
+        double2 r0, r1;
+        rows_s(b_el0, m, r0, r1);
+        return hder(hs, r0, r1);
+    };
     bool waited = lw.flags == nullptr;
     post_arrive(lw);
     for (long long u = (long long)blockIdx.x * wpc + warp; u < 2 * upp; u += (long long)gridDim.x * wpc) {
@@ -595,8 +613,7 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
                 rows_s(b_ph0, sx.m, r0, r1);
                 z2 = hval(hb, r0, r1);
                 z2p = hder(hs, r0, r1);
-                rows_s(b_el0, sx.m, r0, r1);
-                emb = hder(hs, r0, r1) * (dfi + dfj);
+                emb = elec_slope(hs, sx.m) * (dfi + dfj);
             } else {
                 const int tjc = max(tj, 0);
                 double rho_p_from, rho_p_to;
@@ -686,8 +703,7 @@ EAM_UNROLL(2)
                         // majority term as the loop evaluated it (staged rows), to be taken back
                         rows_s(b_ph0, sx.m, r0, r1);
                         const double z2m = hval(hb, r0, r1), z2pm = hder(hs, r0, r1);
-                        rows_s(b_el0, sx.m, r0, r1);
-                        const double rho_p_maj = hder(hs, r0, r1);
+                        const double rho_p_maj = elec_slope(hs, sx.m);
                         const double fpm = -recip * fma(inv_dr, fma(z2pm, recip, rho_p_maj * (dfi + dfj)), -(z2m * (recip * recip)));
                         // the pair as it is: phi[maj][tj], rho'_maj * df_j + rho'_tj * df_i (two 256-bit rows of the monomial block)
                         double z2, z2p;

@@ -398,7 +398,7 @@ extern "C" int misa_b200_destroy(misa_b200_ctx *c) {
     cudaFree(c->d_stepinfo); cudaFreeHost(c->h_stepinfo); cudaFree(c->d_stepinfo_g); cudaFree(c->d_stepinfo_n);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     for (cudaEvent_t e : {c->ev_v1, c->ev_act, c->ev_hx, c->ev_rho, c->ev_hdf}) if (e) cudaEventDestroy(e);
-    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm); cudaFree(c->d_c34); cudaFree(c->d_c56); cudaFree(c->d_mono);
+    cudaFree(c->d_elec); cudaFree(c->d_embed); cudaFree(c->d_phi); cudaFree(c->d_herm); cudaFree(c->d_c34); cudaFree(c->d_c56); cudaFree(c->d_mono); cudaFree(c->d_ea); cudaFree(c->d_es);
     cudaFree(c->d_census); cudaFreeHost(c->h_census); cudaFree(c->d_pmax); cudaFree(c->d_ptmp);
     for (int d = 0; d < 3; d++) for (int dir = 0; dir < 2; dir++) { cudaFree(c->halo[d][dir].d_send); cudaFree(c->halo[d][dir].d_recv); }
     for (int dir = 0; dir < 2; dir++) { cudaFree(c->d_sendbuf[dir]); cudaFree(c->d_recvbuf[dir]); }
@@ -770,9 +770,25 @@ static int build_hermite(misa_b200_ctx *c, const misa_b200_table *elec, const mi
                 b[o] = sp[(size_t)m * 7 + 5]; b[o + 1] = sp[(size_t)m * 7 + 6];
             }
         }
-        cudaFree(c->d_c34); cudaFree(c->d_c56); cudaFree(c->d_mono);
-        c->d_c34 = c->d_c56 = nullptr;
-        c->d_mono = nullptr;
+        cudaFree(c->d_c34); cudaFree(c->d_c56); cudaFree(c->d_mono); cudaFree(c->d_ea); cudaFree(c->d_es);
+        c->d_c34 = c->d_c56 = c->d_ea = nullptr;
+        c->d_mono = c->d_es = nullptr;
+        {   // slope-only lookups (force kernel, embedding term): (s_m, v_{m+1} - v_m) rows and the dense slopes
+            std::vector<double> ea((size_t)ntab * (n + 1) * 2, 0.0), es((size_t)ntab * (n + 1) + 2, 0.0);
+            for (int t = 0; t < ntab; t++) {
+                const double *sp = (t < nt ? elec[t] : phi[t - nt]).spline;
+                for (int m = 0; m <= n; m++) {
+                    const size_t o = (size_t)t * (n + 1) + m;
+                    ea[2 * o] = sp[(size_t)m * 7 + 5];
+                    ea[2 * o + 1] = m < n ? sp[(size_t)(m + 1) * 7 + 6] - sp[(size_t)m * 7 + 6] : 0.0;   // the subtraction the kernels did per pair, same doubles
+                    es[o] = sp[(size_t)m * 7 + 5];
+                }
+            }
+            TRY(dmalloc(&c->d_ea, ea.size() / 2));
+            TRY(dmalloc(&c->d_es, es.size()));
+            CU(cudaMemcpy(c->d_ea, ea.data(), ea.size() * sizeof(double), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(c->d_es, es.data(), es.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
         {
             std::vector<double> w((size_t)ntab * (n + 1) * 4, 0.0);
             for (int t = 0; t < ntab; t++) {
@@ -1232,6 +1248,22 @@ static bool make_plan(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes)
     return smem_bytes + 1024 <= (size_t)c->smem_optin;
 }
 
+// Force launches of the single-species loop (pure boxes and the dilute-alloy variants): slot 0 as (slope, value difference) rows plus
+// the dense slopes of elec[maj] behind the slots (StagePlan::half_src) -- when the extra 8 bytes per row still fit.
+// false: it does not fit -- the caller must not launch a single-species k_force_f (the second-generation kernels take over).
+static bool plan_elec3(const misa_b200_ctx *c, StagePlan &sp, size_t &smem_bytes) {
+#if EAM_ELEC3
+    const int n = c->tab.n_r, maj = sp.staged_id[0], r0 = sp.row_lo & ~1;
+    const size_t bytes = (((size_t)(n + 1 - r0) * 8 + 15) / 16) * 16;
+    if (!c->d_ea || !c->d_es || smem_bytes + bytes + 1024 > (size_t)c->smem_optin) return false;
+    sp.src[0] = c->d_ea + (size_t)maj * (n + 1);
+    sp.half_src = c->d_es + (size_t)maj * (n + 1) + r0;
+    sp.half_bytes = (int)bytes;
+    smem_bytes += bytes;
+#endif
+    return true;
+}
+
 // No vacant site anywhere in the ghost-extended array: true once the census counted every site as valid and no
 // run-away has been seen since (decide() is the only thing that vacates a site; every rank learns of run-aways
 // anywhere through the per-step activity reduction, so a vacancy cannot enter the ghost shell unnoticed).
@@ -1668,7 +1700,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
         if (dil) TRY(launch_force_minor(c, sp, offs, n_off, ls, tex));
         return 0;
     }
-    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum)) {
+    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && dilute_ok(c, sp, accum) && plan_elec3(c, sp, sb)) {
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
         const RegionList rl = regions_for(c, so, late);
@@ -1692,7 +1724,7 @@ static int launch_force(misa_b200_ctx *c, bool accum, const StencilOpt &so = Ste
     }
     // non-dilute alloys: the generic-pointer force variant (three generic row fetches per pair) measured slower than the
     // second generation's staged/divergent one (1.50 vs 1.18 ms at 97:2:1), so multi-species force stays on k_force_s
-    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 || c->opt_fast > 1)) {
+    if (c->opt_fast && c->tex_all && make_plan(c, sp, sb) && (sp.single >= 0 ? plan_elec3(c, sp, sb) : c->opt_fast > 1)) {   // (the multi-species template reads slot 0 as Hermite rows)
         const int grid = std::max(1, c->sm_count - so.reserve_sms);
         const bool novac = no_type_test(c), single = sp.single >= 0;
         const TexAll tex = {c->tex_all, (int)c->xyzd_stride};
