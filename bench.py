@@ -34,7 +34,7 @@ STEP_BYTES_PER_ATOM = 316
 # fp64 view (SURVEY.md section 8d "algorithmic flops"): fp64 warp instructions per EVALUATED pair and per distance test
 # that is rejected, counted in the SASS of the production kernels (profiles/r02_sass_near_loop.txt; DFMA/DMUL/DADD/DSETP/
 # MUFU.RSQ64H each one issue slot of the fp64 pipe); peak = measured DFMA lane rate (profiles/r01_fp64_peak.json)
-FP64_INST = {"force": {"eval": 51, "test": 7}, "rho": {"eval": 22, "test": 7}}
+FP64_INST = {"force": {"eval": 50, "test": 7}, "rho": {"eval": 22, "test": 7}}
 # the stencil kernels whose ncu capture profiles/traffic.json describes; bench.py emits traffic: null when these sources changed
 TRAFFIC_SOURCES = ["misa_md_b200/csrc/eam_fast.cuh", "misa_md_b200/csrc/eam_smem.cuh"]
 

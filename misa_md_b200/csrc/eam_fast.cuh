@@ -36,6 +36,12 @@
 #define EAM_OFF_V4 1   // near group: four staged offsets per 16-byte shared-memory load (0: one 4-byte load per pair)
 #endif
 #define EAM_PRAGMA(x) _Pragma(#x)
+// four staged offsets with ONE 16-byte shared-memory load (p 16-byte aligned)
+__device__ __forceinline__ int4 ld_off4(const int *p) {
+    int4 o;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return o;
+}
 #define EAM_UNROLL(n) EAM_PRAGMA(unroll n)
 
 // 1/sqrt(a) for 0 < a < inf, normal range: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
@@ -156,8 +162,13 @@ __device__ __forceinline__ double mono_fpair(const double *__restrict__ mono, co
 #ifndef EAM_MONO_RHO
 #define EAM_MONO_RHO 1
 #endif
-__device__ __forceinline__ double mono_val_s(const uint32_t base_a, const uint32_t base_b, const int m, const double p) {
+__device__ __forceinline__ double mono_val_s(const uint32_t base_a, const uint32_t base_b, const int m_, const double p) {
     double c3, c4, c5, c6;
+#if EAM_EXP_NOCONFLICT
+    const int m = ((m_ - 7) & ~7) | (int)(threadIdx.x & 7u);   // (measurement only, wrong numbers: see rows_s)
+#else
+    const int m = m_;
+#endif
     const uint32_t o = (uint32_t)m << 4;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c3), "=d"(c4) : "r"(base_a + o));
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c5), "=d"(c6) : "r"(base_b + o));
@@ -453,21 +464,23 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
         };
         const int n_near4 = EAM_OFF_V4 ? (n_near & ~3) : 0;
         for (int q = 0; q < n_near4; q += 4) {
-            const int4 o4 = *reinterpret_cast<const int4 *>(off + q);
+            const int4 o4 = ld_off4(off + q);
             near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
         }
 EAM_UNROLL(EAM_UNROLL_NEAR)
         for (int q = n_near4; q < n_near; q++) near_pair(off[q]);
-EAM_UNROLL(EAM_UNROLL_FAR)
-        for (int q = n_near; q < n_off; q++) {
-            const int j = d + off[q];
+        auto far_pair = [&](const int o) {
+            const int j = d + o;
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
             const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
             if (__any_sync(0xffffffffu, in)) pair(d2, in, tj);
-        }
+        };
+        // (four offsets per load here as in k_force_f was measured: rho 0.3814 -> 0.3836 ms, force 0.6099 -> 0.6060 -- kept there only)
+EAM_UNROLL(EAM_UNROLL_FAR)
+        for (int qf = n_near; qf < n_off; qf++) far_pair(off[qf]);
         bool low = mmin < row_lo;
         if (DILUTE) {
             const int nm = ml.count[d];
@@ -660,21 +673,30 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
         };
         const int n_near4 = EAM_OFF_V4 ? (n_near & ~3) : 0;
         for (int q = 0; q < n_near4; q += 4) {
-            const int4 o4 = *reinterpret_cast<const int4 *>(off + q);
+            const int4 o4 = ld_off4(off + q);
             near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
         }
 EAM_UNROLL(EAM_UNROLL_NEAR)
         for (int q = n_near4; q < n_near; q++) near_pair(off[q]);
-EAM_UNROLL(EAM_UNROLL_FAR)
-        for (int q = n_near; q < n_off; q++) {
-            const int j = d + off[q];
+        auto far_pair = [&](const int o) {
+            const int j = d + o;
             int tj = 0;
             if (NEEDTYPE) tj = s.type[j];
             const double dx = xi - nb_f64<0>(tx, ns, s.x[0], j), dy = yi - nb_f64<1>(tx, ns, s.x[1], j), dz = zi - nb_f64<2>(tx, ns, s.x[2], j);
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2);
             if (__any_sync(0xffffffffu, in)) pair(dx, dy, dz, d2, in, tj, j);
+        };
+        int qf = n_near;
+        if (EAM_OFF_V4) {                                  // up to the next multiple of four, then four offsets per load
+            for (; (qf & 3) && qf < n_off; qf++) far_pair(off[qf]);
+            for (; qf + 4 <= n_off; qf += 4) {
+                const int4 o4 = ld_off4(off + qf);
+                far_pair(o4.x); far_pair(o4.y); far_pair(o4.z); far_pair(o4.w);
+            }
         }
+EAM_UNROLL(EAM_UNROLL_FAR)
+        for (; qf < n_off; qf++) far_pair(off[qf]);
         bool low = mmin < row_lo;
         if (DILUTE) {
             const bool mine = ti == ml.maj;       // minority central atoms: k_force_minor writes them
