@@ -29,6 +29,18 @@
 #ifndef EAM_UNROLL_FAR
 #define EAM_UNROLL_FAR 4
 #endif
+#ifndef EAM_RHO_G8
+#define EAM_RHO_G8 1   // rho kernel: eight near pairs per trip -- twice the neighbour fetches in flight per warp (0.3808 -> 0.3729 ms)
+#endif
+#ifndef EAM_RHO_G16
+#define EAM_RHO_G16 1  // sixteen where the group is long enough (0.3722 -> 0.3666 ms)
+#endif
+#ifndef EAM_FORCE_G8
+#define EAM_FORCE_G8 1 // force kernel: eight near pairs per trip (0.6054 -> 0.5979 ms)
+#endif
+#ifndef EAM_FORCE_G16
+#define EAM_FORCE_G16 0 // (measurement)
+#endif
 #ifndef EAM_ELEC3
 #define EAM_ELEC3 1    // force kernel, single-species loop: slope of elec[maj] from (s_m, dv_m) + s_{m+1} (StagePlan::half_src)
 #endif
@@ -463,12 +475,29 @@ k_rho_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, const 
             pair(d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj);
         };
         const int n_near4 = EAM_OFF_V4 ? (n_near & ~3) : 0;
-        for (int q = 0; q < n_near4; q += 4) {
+        int q = 0;
+#if EAM_RHO_G16
+        for (; q + 16 <= n_near4; q += 16) {
+            const int4 o4 = ld_off4(off + q), o8 = ld_off4(off + q + 4), oc = ld_off4(off + q + 8), og = ld_off4(off + q + 12);
+            near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
+            near_pair(o8.x); near_pair(o8.y); near_pair(o8.z); near_pair(o8.w);
+            near_pair(oc.x); near_pair(oc.y); near_pair(oc.z); near_pair(oc.w);
+            near_pair(og.x); near_pair(og.y); near_pair(og.z); near_pair(og.w);
+        }
+#endif
+#if EAM_RHO_G8
+        for (; q + 8 <= n_near4; q += 8) {                 // eight pairs per trip: twice the fetches in flight per warp
+            const int4 o4 = ld_off4(off + q), o8 = ld_off4(off + q + 4);
+            near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
+            near_pair(o8.x); near_pair(o8.y); near_pair(o8.z); near_pair(o8.w);
+        }
+#endif
+        for (; q < n_near4; q += 4) {
             const int4 o4 = ld_off4(off + q);
             near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
         }
 EAM_UNROLL(EAM_UNROLL_NEAR)
-        for (int q = n_near4; q < n_near; q++) near_pair(off[q]);
+        for (q = n_near4; q < n_near; q++) near_pair(off[q]);
         auto far_pair = [&](const int o) {
             const int j = d + o;
             int tj = 0;
@@ -672,12 +701,29 @@ k_force_f(const Geo g, const Soa s, const DevTables tb, const StagePlan sp, cons
             pair(dx, dy, dz, d2, NEEDTYPE ? (tj >= 0 && d2 < rc2) : (d2 < rc2), tj, j);
         };
         const int n_near4 = EAM_OFF_V4 ? (n_near & ~3) : 0;
-        for (int q = 0; q < n_near4; q += 4) {
+        int q = 0;
+#if EAM_FORCE_G16
+        for (; q + 16 <= n_near4; q += 16) {
+            const int4 o4 = ld_off4(off + q), o8 = ld_off4(off + q + 4), oc = ld_off4(off + q + 8), og = ld_off4(off + q + 12);
+            near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
+            near_pair(o8.x); near_pair(o8.y); near_pair(o8.z); near_pair(o8.w);
+            near_pair(oc.x); near_pair(oc.y); near_pair(oc.z); near_pair(oc.w);
+            near_pair(og.x); near_pair(og.y); near_pair(og.z); near_pair(og.w);
+        }
+#endif
+#if EAM_FORCE_G8
+        for (; q + 8 <= n_near4; q += 8) {
+            const int4 o4 = ld_off4(off + q), o8 = ld_off4(off + q + 4);
+            near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
+            near_pair(o8.x); near_pair(o8.y); near_pair(o8.z); near_pair(o8.w);
+        }
+#endif
+        for (; q < n_near4; q += 4) {
             const int4 o4 = ld_off4(off + q);
             near_pair(o4.x); near_pair(o4.y); near_pair(o4.z); near_pair(o4.w);
         }
 EAM_UNROLL(EAM_UNROLL_NEAR)
-        for (int q = n_near4; q < n_near; q++) near_pair(off[q]);
+        for (q = n_near4; q < n_near; q++) near_pair(off[q]);
         auto far_pair = [&](const int o) {
             const int j = d + o;
             int tj = 0;
